@@ -1,0 +1,270 @@
+"""bench.py - utterances/s of the speaker-conditioned mask-estimation forward pass on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (CNN -> BiLSTM -> FC -> sigmoid mask -> mask * spectrogram)
+over one batch of synthetic utterances.  Workload (BASELINE.json): `--batch` utterances per GPU of
+601 frames x 257 bins + a random 256-d d-vector, random-init ("stress" flavour) weights of the
+reference architecture.  Utterances are independent, so the batch is sharded across ranks with no
+data-path collective (weak scaling; the only collective is the max-over-ranks of the timings).
+
+One JSON line is printed by rank 0; keys are documented in DESIGN.md ("Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from voicesplit_b200 import synth  # noqa: E402
+
+# algorithmic forward FLOPs (2 x MAC) per utterance, SURVEY.md section 8(d)
+def flops_per_utt(T, F, E=256, H=400, N1=600):
+    P = T * F
+    conv = 2 * P * (64 * 7 + 64 * 64 * 7 + 5 * 64 * 64 * 25 + 64 * 8)
+    lstm = 2 * T * (8 * F * 8 * H) + 2 * (E * 8 * H) + 2 * T * 2 * (H * 4 * H)
+    fc = 2 * T * (2 * H * N1 + N1 * F)
+    return dict(conv=conv, conv5x5_layer=2 * P * 64 * 64 * 25, lstm=lstm, fc=fc, total=conv + lstm + fc)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json (of measured)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="B200_PROFILING.md fallback (of fallback)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_throughput(dims, T, seconds_budget=20.0, steps=1, warmup=1):
+    """The reference's CPU implementation of the path (torch.nn ops == oracle/torch_port.py, all host
+    threads) on a bounded sample of the workload: B_s utterances of the same T x F."""
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_state_dict(dims, 0, "stress").items() if v.dtype == np.float32}
+    bs = 1
+    x, emb = synth.make_inputs(bs, T, dims, 99)
+    xt, et = torch.from_numpy(x), torch.from_numpy(emb)
+    t0 = time.perf_counter()
+    torch_port.forward(sd, xt, et)                      # warm-up (also sizes the sample)
+    one = time.perf_counter() - t0
+    bs = int(max(1, min(8, (seconds_budget / max(steps + warmup - 1, 1)) // max(one, 1e-3))))
+    x, emb = synth.make_inputs(bs, T, dims, 99)
+    xt, et = torch.from_numpy(x), torch.from_numpy(emb)
+    for _ in range(max(warmup - 1, 0)):
+        torch_port.forward(sd, xt, et)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        torch_port.forward(sd, xt, et)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.sum(times))
+    return dict(value=bs * steps / dt, unit="utterances/s", cores=cores, kind="port",
+                sample=f"{bs} utterance(s) x {steps} step(s) of {T}x{dims['num_freq']} through oracle/torch_port.py "
+                       f"(the reference's own torch.nn CPU ops, fp32, {cores} threads), {dt:.1f} s"), dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("VOICESPLIT_PRECISION", "bf16x3"))
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=601)
+    ap.add_argument("--freq", type=int, default=257)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dims = synth.make_dims(args.freq, 256, 400, 600)
+    T, F, B = args.frames, args.freq, args.batch
+    fl = flops_per_utt(T, F)
+    workload = f"full forward CNN+BiLSTM+FC+mask apply, {B} utt/GPU x {T} frames x {F} bins + 256-d d-vector (BASELINE configs[2] shape)"
+    config = {"workload": workload, "per_gpu_batch": B, "frames": T, "freq_bins": F, "global_batch": B * world,
+              "parallelism": f"utterance-sharded x{world}, no data-path collective",
+              "l2_policy": "inputs larger than L2 (x is %.0f MB per step)" % (B * T * F * 4 / 1e6),
+              "weights": "random-init stress flavour (synth.make_state_dict seed 0)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, step_s = cpu_reference_throughput(dims, T, seconds_budget=60.0, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+        line = {"impl": "reference", "metric": "utterances/s (601-frame, 257-bin spectrogram) masked", "value": cb["value"],
+                "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    from voicesplit_b200.engine import MaskEngine
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = MaskEngine(activation="mish", device=dev, **dims)
+    sd = synth.make_state_dict(dims, 0, "stress")
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).to(dev) for k, v in sd.items() if v.dtype == np.float32})
+    xh, eh = synth.make_inputs(B, T, dims, 1234 + rank)
+    xh, eh = torch.from_numpy(xh).pin_memory(), torch.from_numpy(eh).pin_memory()
+    x, emb = xh.to(dev), eh.to(dev)
+    mask_h, masked_h = torch.empty_like(xh).pin_memory(), torch.empty_like(xh).pin_memory()
+    prec = args.precision
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        eng.forward(x, emb, precision=prec, want_masked=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = {}
+    ev0.record()
+    for _ in range(args.steps):
+        eng.forward(x, emb, precision=prec, want_masked=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    for name, ms in eng.profile_read():           # per-kernel times of the last timed step
+        kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
+    launches_per_step = eng.last_launch_count()
+    eng.set_profiling(False)
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    barrier()
+    # ---- end to end through the host-buffer plugin call ("e2e")
+    for _ in range(min(args.warmup, 2)):
+        eng.forward_host(xh, eh, mask_h, masked_h, precision=prec)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.forward_host(xh, eh, mask_h, masked_h, precision=prec)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = B * world * args.steps / (dev_ms / 1e3)
+        e2e_value = B * world * args.steps / (e2e_ms / 1e3)
+        # dominant kernel: the five 5x5 dilated conv layers (89.5 % of the algorithmic FLOPs)
+        conv_ms = [kernel_ms.get(f"cnn{i}") for i in (3, 4, 5, 6, 7)]
+        roof = None
+        if all(v is not None for v in conv_ms):
+            avg = float(np.mean(conv_ms))
+            ach = fl["conv5x5_layer"] * B / (avg / 1e3) / 1e12
+            passes = {"bf16x3": 3, "bf16": 1}.get(prec)
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "kernel": "dilated 5x5 conv 64->64 + BN + act (cnn3..cnn7)", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                    "avg_launch_ms": avg, "algorithmic_flops_per_launch": fl["conv5x5_layer"] * B,
+                    "mma_passes": passes, "tensor_pipe_frac_incl_passes": (ach * passes / peak) if passes else None,
+                    "note": "fp32 mode runs on CUDA cores (no tensor pipe)" if prec == "fp32" else None}
+        line = {"metric": "utterances/s (601-frame, 257-bin spectrogram) masked", "value": value, "unit": "utterances/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[prec],
+                "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "utterances/s", "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": int(xh.numel() * 4 + eh.numel() * 4),
+                        "d2h_bytes_per_step": int(mask_h.numel() * 4 + masked_h.numel() * 4)},
+                "gpu_launches": launches_per_step * args.steps * 2,   # device-resident + e2e timed regions
+                "launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roof,
+                "kernel_ms_last_step": {k: round(v, 4) for k, v in kernel_ms.items()},
+                "gflop_per_utt": {k: v / 1e9 for k, v in fl.items()},
+                "tflops_total_algorithmic": fl["total"] * value / 1e12}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_throughput(dims, T, seconds_budget=20.0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,143 @@
+/*
+ * voicesplit_b200 - C ABI of the B200 (sm_100a) mask-estimation engine.
+ *
+ * The reference (Edresson/VoiceSplit) has no FFI or plugin interface: its boundary for this
+ * path is the Python nn.Module contract.  This header is therefore the
+ * seam *beneath* that contract: the repo's own models/voicesplit/model.py and
+ * models/voicefilter/model.py (same class names, constructor, forward signature and state_dict
+ * as /root/reference/models/voicesplit/model.py:9-89 and
+ * /root/reference/models/voicefilter/model.py:11-90) bind exactly these entry points through
+ * ctypes (voicesplit_b200/_cabi.py).  INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; every function returns VS_OK (0) or a negative
+ * VS_ERR_* code and never throws; vs_last_error() gives the message for the calling thread.
+ * Device pointers are CUDA device memory of the current device; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  No function allocates device memory on the
+ * hot call (vs_forward / vs_conv_stack): parameters are packed once by vs_engine_load_params
+ * and scratch space is a caller-provided workspace of vs_workspace_bytes().
+ */
+#ifndef VOICESPLIT_B200_H
+#define VOICESPLIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_ABI_VERSION 1
+
+#define VS_OK 0
+#define VS_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define VS_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define VS_ERR_STATE (-3)       /* parameters not loaded, workspace too small, ... */
+#define VS_ERR_UNSUPPORTED (-4) /* feature not built for this device (needs sm_100a) */
+
+/* activation after each BatchNorm: Mish = VoiceSplit (reference utils/generic_utils.py:395-399),
+ * ReLU = VoiceFilter (reference models/voicefilter/model.py:21) */
+#define VS_ACT_MISH 0
+#define VS_ACT_RELU 1
+
+/* arithmetic of the contractions (conv stack, LSTM input projection, FC head):
+ *   FP32    fp32 FFMA on CUDA cores - exact-order-independent fp32, the on-GPU ground truth
+ *   BF16X3  tcgen05 tensor cores, operands split a = hi + lo (bf16 each), three MMAs
+ *           (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator: ~2^-16 relative operand error
+ *   BF16    tcgen05 tensor cores, single bf16 pass (fast mode; error reported, not hidden) */
+#define VS_PREC_FP32 0
+#define VS_PREC_BF16X3 1
+#define VS_PREC_BF16 2
+
+typedef struct vs_engine vs_engine;
+
+/* mirrors the config.json keys the reference module reads (reference config.json:36-41,86;
+ * models/voicesplit/model.py:13,58-64) */
+typedef struct vs_dims {
+    int32_t num_freq; /* audio[backend].num_freq, F */
+    int32_t emb_dim;  /* model.emb_dim, E */
+    int32_t lstm_dim; /* model.lstm_dim, H */
+    int32_t fc1_dim;  /* model.fc1_dim */
+    int32_t fc2_dim;  /* model.fc2_dim, must equal num_freq */
+    int32_t activation; /* VS_ACT_* */
+} vs_dims;
+
+/* Device pointers to the fp32 parameters in the reference's state_dict layout:
+ * conv l=0..7 are Sequential positions 1,5,9,13,17,21,25,28; bn l the BatchNorm after it. */
+typedef struct vs_params {
+    const float* conv_w[8];  /* [Cout][Cin][kh][kw] */
+    const float* conv_b[8];  /* [Cout] */
+    const float* bn_gamma[8];
+    const float* bn_beta[8];
+    const float* bn_mean[8]; /* running_mean */
+    const float* bn_var[8];  /* running_var  */
+    const float* w_ih[2];    /* [4H][8F+E], direction 0 = forward, 1 = reverse */
+    const float* w_hh[2];    /* [4H][H] */
+    const float* b_ih[2];    /* [4H] */
+    const float* b_hh[2];    /* [4H] */
+    const float* fc1_w;      /* [fc1][2H] */
+    const float* fc1_b;
+    const float* fc2_w;      /* [F][fc1] */
+    const float* fc2_b;
+} vs_params;
+
+int vs_abi_version(void);
+const char* vs_last_error(void);
+
+/* Engine life cycle.  vs_engine_create selects the current CUDA device and fails with
+ * VS_ERR_UNSUPPORTED if it is not compute capability 10.x. */
+int vs_engine_create(const vs_dims* dims, vs_engine** out);
+int vs_engine_destroy(vs_engine* e);
+
+/* Fold eval-mode BatchNorm into per-channel scale/shift, repack the weights into the kernels'
+ * layouts (fp32 + bf16 hi/lo planes, tap-pair-major for the tensor-core conv).  Must be called
+ * again whenever the parameters change (optimizer step, load_state_dict). */
+int vs_engine_load_params(vs_engine* e, const vs_params* device_params, void* stream);
+
+/* Scratch bytes vs_forward / vs_conv_stack need for a batch of B utterances of T frames. */
+size_t vs_workspace_bytes(const vs_engine* e, int32_t B, int32_t T, int32_t precision);
+
+/* The hot path: reference VoiceSplit.forward (models/voicesplit/model.py:66-89) plus the
+ * caller-side mask apply (train.py:95).
+ *   x      [B][T][F] fp32 device, spectrogram magnitudes
+ *   emb    [B][E]    fp32 device, d-vectors
+ *   mask   [B][T][F] fp32 device, out
+ *   masked [B][T][F] fp32 device, out, x*mask; may be NULL */
+int vs_forward(vs_engine* e, const float* x, const float* emb, float* mask, float* masked,
+               int32_t B, int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies x/emb to the device, runs vs_forward,
+ * copies mask (and masked) back and synchronises the stream.  The engine keeps a grow-only
+ * device staging area for this entry point, so repeated calls of the same shape do not allocate. */
+int vs_forward_host(vs_engine* e, const float* x_host, const float* emb_host, float* mask_host,
+                    float* masked_host, int32_t B, int32_t T, int32_t precision, void* stream);
+
+/* Conv stack only (reference model.conv + the transpose/view of model.py:70-74):
+ * x [B][T][F] -> conv_out [B][T][8F] fp32 device (index c*F+f). */
+int vs_conv_stack(vs_engine* e, const float* x, float* conv_out, int32_t B, int32_t T,
+                  int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hooks: run a single conv layer l (0..6 -> 64-channel output) on an fp32 NCHW input
+ * in [B][Cin][T][F] -> out [B][64][T][F], and the BiLSTM + head on a given conv_out.
+ * They allocate internally and synchronise; not for the hot path. */
+int vs_debug_conv_layer(vs_engine* e, int32_t layer, const float* in_nchw, float* out_nchw,
+                        int32_t B, int32_t T, int32_t precision, void* stream);
+int vs_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, const float* x,
+                       float* lstm_out, float* mask, int32_t B, int32_t T, int32_t precision,
+                       void* stream);
+
+/* Number of kernels this library launched during the last vs_forward / vs_conv_stack. */
+int vs_last_launch_count(const vs_engine* e);
+
+/* Per-kernel device timing of the last vs_forward / vs_conv_stack: when enabled, a CUDA event is
+ * recorded on the launch stream after every kernel.  vs_profile_read waits for the last event and
+ * returns the number of entries written (kernel id, milliseconds); ids: 0 cnn1, 1..6 cnn2..cnn7,
+ * 7 cnn8+reshape, 8 d-vector gate bias, 9 LSTM input projection, 10 LSTM recurrence, 11 fc1,
+ * 12 fc2+sigmoid+mask, 13 layout/precision conversion, 14 fused head. */
+int vs_engine_set_profiling(vs_engine* e, int32_t enabled);
+int vs_profile_read(vs_engine* e, int32_t max_entries, int32_t* kernel_ids, float* milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOICESPLIT_B200_H */

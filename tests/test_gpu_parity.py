@@ -1,0 +1,144 @@
+"""Parity tests proper (need the B200): the CUDA path, called through the C ABI, against the
+committed golden vectors (outputs of the unmodified reference) and against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): mask within 1e-3 of the reference; we assert
+max |diff| < 1e-3 and mean |diff| (MAE) < 1e-4 for the fp32-faithful modes (fp32, bf16x3), and
+report - with a looser, explicitly stated bound - the single-pass bf16 fast mode.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases, load_case
+from oracle import oracle
+from voicesplit_b200 import config, synth
+from voicesplit_b200.engine import MaskEngine
+
+pytestmark = pytest.mark.gpu
+
+FAITHFUL = ["fp32", "bf16x3"]
+TOL_MAX = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 2.5e-1}
+TOL_MAE = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 3e-2}
+
+
+def _engine(case):
+    eng = MaskEngine(activation="mish" if case["model_name"] == "voicesplit" else "relu", **case["dims"])
+    eng.load_state_dict_tensors({k: torch.from_numpy(np.asarray(v)).cuda() for k, v in case["state_dict"].items()
+                                 if "num_batches" not in k})
+    return eng
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_mask_matches_reference_golden(golden, precision):
+    eng = _engine(golden)
+    x, emb = torch.from_numpy(golden["x"]).cuda(), torch.from_numpy(golden["emb"]).cuda()
+    mask, masked = eng.forward(x, emb, precision=precision, want_masked=True)
+    torch.cuda.synchronize()
+    d = (mask.cpu().numpy() - golden["mask"])
+    assert np.isfinite(d).all()
+    assert np.abs(d).max() < TOL_MAX[precision], (np.abs(d).max(), np.abs(d).mean())
+    assert np.abs(d).mean() < TOL_MAE[precision]
+    assert np.abs(masked.cpu().numpy() - golden["masked"]).max() < TOL_MAX[precision]
+    assert eng.last_launch_count() > 0
+
+
+@pytest.mark.parametrize("precision", FAITHFUL)
+def test_conv_stack_matches_golden(golden, precision):
+    eng = _engine(golden)
+    out = eng.conv_stack(torch.from_numpy(golden["x"]).cuda(), precision=precision).cpu().numpy()
+    ref = golden["conv_out"]
+    assert np.abs(out - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("precision", FAITHFUL)
+def test_lstm_and_head_match_golden(golden, precision):
+    eng = _engine(golden)
+    conv = torch.from_numpy(golden["conv_out"]).cuda()
+    lstm_out, mask = eng.debug_lstm_head(conv, torch.from_numpy(golden["emb"]).cuda(),
+                                         torch.from_numpy(golden["x"]).cuda(), precision=precision)
+    assert np.abs(lstm_out.cpu().numpy() - golden["lstm_out"]).max() < 1e-3
+    assert np.abs(mask.cpu().numpy() - golden["mask"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("layer", [1, 2, 4, 6])
+def test_single_conv_layer_against_oracle(layer, precision):
+    """One dilated conv + BN + Mish layer on random 64-channel input, against the oracle's layer."""
+    dims = synth.make_dims(41, 8, 16, 24)
+    sd = synth.make_state_dict(dims, 21, "stress")
+    B, T, F = 2, 45, 41
+    rng = np.random.default_rng(layer)
+    inp = rng.uniform(-1, 1, size=(B, 64, T, F)).astype(np.float32)
+    eng = MaskEngine(activation="mish", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    got = eng.debug_conv_layer(layer, torch.from_numpy(inp).cuda(), precision=precision).cpu().numpy()
+    # oracle for one layer: torch-free restatement via the C oracle is whole-path only, so use
+    # float64 numpy here (same formula as oracle/voicesplit_oracle.c conv_bn_act)
+    idx, cin, cout, kh, kw, dil = synth.CONV_LAYERS[layer]
+    w = sd[f"conv.{idx}.weight"].astype(np.float64); bn = synth.BN_INDEX[idx]
+    pt, pf = (kh - 1) // 2 * dil, (kw - 1) // 2
+    xp = np.pad(inp.astype(np.float64), ((0, 0), (0, 0), (pt, pt), (pf, pf)))
+    acc = np.zeros((B, cout, T, F))
+    for i in range(kh):
+        for j in range(kw):
+            acc += np.einsum("oc,bctf->botf", w[:, :, i, j], xp[:, :, i * dil:i * dil + T, j:j + F])
+    acc += sd[f"conv.{idx}.bias"].astype(np.float64)[None, :, None, None]
+    g, b_, m, v = (sd[f"conv.{bn}.{k}"].astype(np.float64)[None, :, None, None]
+                   for k in ("weight", "bias", "running_mean", "running_var"))
+    y = (acc - m) * g / np.sqrt(v + 1e-5) + b_
+    ref = oracle.activation(y.astype(np.float32), "mish")
+    tol = {"fp32": 2e-4, "bf16x3": 2e-4, "bf16": 1e-1}[precision]
+    assert np.abs(got - ref).max() < tol * max(1.0, np.abs(ref).max())
+
+
+def test_module_forward_matches_golden_and_repacks_after_update():
+    case = load_case([p for p in golden_cases() if "tiny_mish_stress" in p][0])
+    from models.voicesplit.model import VoiceSplit
+    m = VoiceSplit(config.AttrDict(synth.make_config_dict(case["dims"])))
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in case["state_dict"].items()})
+    m = m.cuda().eval()
+    x, emb = torch.from_numpy(case["x"]).cuda(), torch.from_numpy(case["emb"]).cuda()
+    with torch.no_grad():
+        mask = m(x, emb)
+    assert mask.shape == x.shape and mask.device == x.device
+    assert np.abs(mask.cpu().numpy() - case["mask"]).max() < 1e-3
+    with torch.no_grad():                      # an in-place parameter update must invalidate the packing
+        m.fc2.bias.add_(3.0)
+        mask2 = m(x, emb)
+    assert (mask2 > mask).float().mean() > 0.99
+    with pytest.raises(NotImplementedError):
+        m.train()(x, emb)
+
+
+@pytest.mark.parametrize("precision", FAITHFUL)
+def test_full_size_against_oracle(precision):
+    """BASELINE shapes: native 301x601 and literal 601x257, B=1, stress weights, vs the CPU oracle."""
+    for dims, T in ((synth.make_dims(257), 601), (synth.make_dims(601), 301)):
+        sd = synth.make_state_dict(dims, 31, "stress")
+        x, emb = synth.make_inputs(1, T, dims, 41)
+        ref = oracle.forward(sd, dims, x, emb)["mask"]
+        eng = MaskEngine(activation="mish", **dims)
+        eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+        got = eng.forward(torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda(), precision=precision).cpu().numpy()
+        d = np.abs(got - ref)
+        assert d.max() < 1e-3 and d.mean() < 1e-4, (dims["num_freq"], d.max(), d.mean())
+
+
+def test_batch_independence_and_host_entry():
+    """Size-independent properties at a bigger batch: utterances are independent (a batch equals
+    its utterances run one by one) and the host-buffer entry point equals the device one."""
+    dims = synth.make_dims(65, 32, 48, 64)
+    sd = synth.make_state_dict(dims, 5, "stress")
+    eng = MaskEngine(activation="mish", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    x, emb = synth.make_inputs(5, 77, dims, 3)
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
+    for precision in ("fp32", "bf16x3"):
+        full = eng.forward(xt, et, precision=precision)
+        for b in (0, 4):
+            one = eng.forward(xt[b:b + 1], et[b:b + 1], precision=precision)
+            assert torch.allclose(full[b:b + 1], one, atol=2e-6, rtol=0)
+        xh, eh = torch.from_numpy(x).pin_memory(), torch.from_numpy(emb).pin_memory()
+        mh = torch.empty_like(xh).pin_memory()
+        eng.forward_host(xh, eh, mh, precision=precision)
+        assert torch.equal(mh, full.cpu())

@@ -46,3 +46,10 @@ def test_oracle_matches_live_reference_train_shape():
         ref = model(torch.from_numpy(x), torch.from_numpy(emb)).numpy()
     got = oracle.forward(sd, dims, x, emb)["mask"]
     assert np.abs(got - ref).max() < 1e-3 and np.abs(got - ref).mean() < 2e-5
+
+
+def test_torch_port_matches_reference_goldens(golden):
+    """The multi-threaded CPU baseline (oracle/torch_port.py) against the same golden vectors."""
+    from oracle import torch_port
+    got = torch_port.forward(golden["state_dict"], golden["x"], golden["emb"], golden["model_name"]).numpy()
+    assert np.abs(got - golden["mask"]).max() < 2e-5

@@ -1,0 +1,80 @@
+"""ctypes binding of include/voicesplit_b200.h (the C ABI of libvoicesplit_sm100.so).
+
+There is deliberately no fallback: if the shared library is missing or a symbol is absent the
+import raises, so a GPU box can never silently run a different implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvoicesplit_sm100.so")
+
+VS_OK = 0
+ACT_MISH, ACT_RELU = 0, 1
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+_fp = ctypes.POINTER(ctypes.c_float)
+
+
+class VsDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("num_freq", "emb_dim", "lstm_dim", "fc1_dim", "fc2_dim", "activation")]
+
+
+class VsParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * 8) for n in
+                ("conv_w", "conv_b", "bn_gamma", "bn_beta", "bn_mean", "bn_var")] + \
+               [(n, ctypes.c_void_p * 2) for n in ("w_ih", "w_hh", "b_ih", "b_hh")] + \
+               [(n, ctypes.c_void_p) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+# name -> (restype, argtypes); must list every function include/voicesplit_b200.h declares
+_VP, _I, _SZ = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
+SIGNATURES = {
+    "vs_abi_version": (ctypes.c_int, []),
+    "vs_last_error": (ctypes.c_char_p, []),
+    "vs_engine_create": (ctypes.c_int, [ctypes.POINTER(VsDims), ctypes.POINTER(_VP)]),
+    "vs_engine_destroy": (ctypes.c_int, [_VP]),
+    "vs_engine_load_params": (ctypes.c_int, [_VP, ctypes.POINTER(VsParams), _VP]),
+    "vs_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "vs_forward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
+    "vs_forward_host": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
+    "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "vs_last_launch_count": (ctypes.c_int, [_VP]),
+    "vs_engine_set_profiling": (ctypes.c_int, [_VP, _I]),
+    "vs_profile_read": (ctypes.c_int, [_VP, _I, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m voicesplit_b200.build` "
+                "(there is no CPU or PyTorch fallback for the mask path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class VsError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != VS_OK:
+        msg = load().vs_last_error()
+        raise VsError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,129 @@
+// Shared device helpers and the engine's internal declarations.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/voicesplit_b200.h"
+
+namespace vs {
+
+// ---- conv stack geometry: reference models/voicesplit/model.py:15-52 --------------------------
+struct ConvGeom { int cin, cout, kh, kw, dil; };
+static constexpr ConvGeom kConv[8] = {
+    {1, 64, 1, 7, 1},  {64, 64, 7, 1, 1}, {64, 64, 5, 5, 1}, {64, 64, 5, 5, 2},
+    {64, 64, 5, 5, 4}, {64, 64, 5, 5, 8}, {64, 64, 5, 5, 16}, {64, 8, 1, 1, 1}};
+
+constexpr int kC = 64;  // channels of the hidden conv planes
+
+// Padded row length of the channels-last activation planes [B][T][Fp][64]: at least two zero
+// pixels after every row so that a +-2 shift along F in the flattened pixel index reads zeros
+// (the reference's ZeroPad2d), rounded to 8 pixels for alignment.
+__host__ __device__ inline int padded_freq(int F) { return ((F + 2 + 7) / 8) * 8; }
+
+// ---- activations -------------------------------------------------------------------------------
+// Mish: x * tanh(softplus(x)), softplus threshold 20 (reference utils/generic_utils.py:399).
+// tanh(log(1+e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = (e^2 + 2e) / (e^2 + 2e + 2); one exp, one divide.
+__device__ __forceinline__ float mish_f(float x) {
+    if (x > 20.f) return x;  // tanh(x) == 1.0f in fp32 for x > 20 (and avoids e^2 overflow)
+    float e = __expf(x);
+    float n = e * (e + 2.f);
+    return x * __fdividef(n, n + 2.f);
+}
+__device__ __forceinline__ float mish_precise(float x) {
+    if (x > 20.f) return x;
+    float e = expf(x);
+    float n = e * (e + 2.f);
+    return x * (n / (n + 2.f));
+}
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+    if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
+    return mish_precise(x);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const std::string& msg);
+#define VS_CUDA_TRY(expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            vs::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                          ":" + std::to_string(__LINE__) + ")");                               \
+            return VS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace vs
+
+// ---- the engine --------------------------------------------------------------------------------
+struct vs_engine {
+    vs_dims d;
+    int device = 0, num_sms = 0;
+    bool loaded = false;
+    int launches = 0;
+
+    // packed parameters (device, owned)
+    float* conv_w32[8] = {};    // fp32 [tap][ci][co]
+    float* conv_scale[8] = {};  // gamma / sqrt(var + eps)
+    float* conv_shift[8] = {};  // (bias - mean) * scale + beta
+    float* wih_x = nullptr;     // fp32 [8H][8F]   both directions stacked, spectrogram columns
+    float* wih_e = nullptr;     // fp32 [8H][E]    d-vector columns
+    float* b_lstm = nullptr;    // fp32 [8H]       b_ih + b_hh
+    float* whh = nullptr;       // fp32 [2][4H][H]
+    float* fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;
+
+    // host staging for vs_forward_host (grow-only)
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+
+    // tensor-core path state (tc_*.cu)
+    void* tc = nullptr;
+
+    // optional per-kernel timing (vs_engine_set_profiling): events recorded after every launch
+    bool profiling = false;
+    void* prof = nullptr;
+};
+
+namespace vs {
+
+// kernel ids reported by vs_profile_read
+enum KernelId {
+    KID_FRONT = 0, KID_CONV1 = 1 /* +layer-1 for layers 1..6 */, KID_POINT8 = 7, KID_EMB_BIAS = 8, KID_INPROJ = 9,
+    KID_LSTM_REC = 10, KID_FC1 = 11, KID_FC2 = 12, KID_CONVERT = 13, KID_HEAD = 14
+};
+void prof_begin(vs_engine* e, cudaStream_t st);
+void prof_after(vs_engine* e, int id, cudaStream_t st);
+#define VS_LAUNCH(e, id, st, call)                                                             \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            vs::set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                 \
+            return VS_ERR_CUDA;                                                                \
+        }                                                                                      \
+        (e)->launches++;                                                                       \
+        if ((e)->profiling) vs::prof_after((e), (id), (st));                                   \
+    } while (0)
+
+// fp32 kernels (fp32_kernels.cu); all launch on `st` and return a cudaError_t
+cudaError_t launch_front_fp32(const vs_engine* e, const float* x, float* plane, int B, int T, cudaStream_t st);
+cudaError_t launch_conv_fp32(const vs_engine* e, int layer, const float* in, float* out, int B, int T, cudaStream_t st);
+cudaError_t launch_point8_fp32(const vs_engine* e, const float* plane, float* xcat, int B, int T, cudaStream_t st);
+// C[M][N] = op(A[M][K]) * W[N][K]^T + bias ; see fp32_kernels.cu
+enum GemmEpi { EPI_NONE = 0, EPI_RELU = 1, EPI_SIGMOID_MASK = 2 };
+cudaError_t launch_gemm_fp32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                             const float* bias_group, int group_rows, float* C, int ldc, int M, int N, int K,
+                             bool relu_a, GemmEpi epi, const float* xmul, float* masked, cudaStream_t st);
+cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float* hout, float* hx,
+                                 unsigned int* barrier, int B, int T, cudaStream_t st);
+size_t lstm_rec_scratch_bytes(const vs_engine* e, int B);
+// layout converters for the debug hooks
+cudaError_t launch_nchw_to_plane(const float* nchw, float* plane, int B, int C, int T, int F, cudaStream_t st);
+cudaError_t launch_plane_to_nchw(const float* plane, float* nchw, int B, int C, int T, int F, cudaStream_t st);
+
+}  // namespace vs

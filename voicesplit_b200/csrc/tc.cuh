@@ -1,0 +1,28 @@
+// Tensor-core (tcgen05 / TMEM / TMA) path of the engine: interface used by engine.cu.
+#pragma once
+#include "common.cuh"
+
+namespace vs {
+
+struct TcLstmBuffers {  // recurrent-kernel buffers shared with the fp32 path (carved by engine.cu)
+    float* gates;       // [B*T][8H]
+    float* bias_u;      // [B][8H]
+    float* hout;        // [B][T][2H]
+    float* hx;          // recurrent exchange + cell state
+    unsigned int* barrier;
+};
+
+int tc_create(vs_engine* e);
+void tc_destroy(vs_engine* e);
+int tc_pack(vs_engine* e, cudaStream_t st);  // after the fp32 packing of vs_engine_load_params
+size_t tc_workspace_bytes(const vs_engine* e, int B, int T, int precision);
+int tc_forward(vs_engine* e, const float* x, const float* emb, float* mask, float* masked, int B, int T,
+               int precision, void* ws, const TcLstmBuffers& lb, cudaStream_t st);
+int tc_conv_stack(vs_engine* e, const float* x, float* conv_out, int B, int T, int precision, void* ws, cudaStream_t st);
+// single layer on fp32 planes (converted to/from the bf16 hi/lo planes internally)
+int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_in, float* plane_out, int B, int T,
+                   int precision, cudaStream_t st);
+int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, const float* x, float* mask, int B, int T,
+                       int precision, const TcLstmBuffers& lb, cudaStream_t st);
+
+}  // namespace vs

@@ -1,0 +1,174 @@
+"""Host-side wrapper of the C-ABI engine: owns the handle, keeps the packed parameters in sync
+with a state dict of torch CUDA tensors, and provides the workspace from torch's caching
+allocator.  PyTorch is used for device memory and streams only; all arithmetic of the mask path
+runs inside libvoicesplit_sm100.so."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _cabi
+
+CONV_IDX = (1, 5, 9, 13, 17, 21, 25, 28)   # nn.Sequential positions (reference model.py:15-52)
+BN_IDX = (2, 6, 10, 14, 18, 22, 26, 29)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class MaskEngine:
+    def __init__(self, num_freq, emb_dim, lstm_dim, fc1_dim, fc2_dim, activation="mish", device=None):
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("voicesplit_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dims = dict(num_freq=num_freq, emb_dim=emb_dim, lstm_dim=lstm_dim, fc1_dim=fc1_dim, fc2_dim=fc2_dim)
+        self.activation = activation
+        d = _cabi.VsDims(num_freq, emb_dim, lstm_dim, fc1_dim, fc2_dim,
+                         _cabi.ACT_MISH if activation == "mish" else _cabi.ACT_RELU)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.vs_engine_create(ctypes.byref(d), ctypes.byref(h)), "vs_engine_create")
+        self.handle = h
+        self._ws = None
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vs_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def load_state_dict_tensors(self, sd):
+        """sd: {reference state_dict key: fp32 CUDA tensor}.  Folds BN, repacks, uploads."""
+        def g(k):
+            t = sd[k]
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.detach().to(self.device, torch.float32).contiguous()
+            return t
+        keep = []
+        p = _cabi.VsParams()
+        for l in range(8):
+            for field, key in (("conv_w", f"conv.{CONV_IDX[l]}.weight"), ("conv_b", f"conv.{CONV_IDX[l]}.bias"),
+                               ("bn_gamma", f"conv.{BN_IDX[l]}.weight"), ("bn_beta", f"conv.{BN_IDX[l]}.bias"),
+                               ("bn_mean", f"conv.{BN_IDX[l]}.running_mean"), ("bn_var", f"conv.{BN_IDX[l]}.running_var")):
+                t = g(key); keep.append(t)
+                getattr(p, field)[l] = t.data_ptr()
+        for d, sfx in enumerate(("", "_reverse")):
+            for field, key in (("w_ih", "weight_ih"), ("w_hh", "weight_hh"), ("b_ih", "bias_ih"), ("b_hh", "bias_hh")):
+                t = g(f"lstm.{key}_l0{sfx}"); keep.append(t)
+                getattr(p, field)[d] = t.data_ptr()
+        for field, key in (("fc1_w", "fc1.weight"), ("fc1_b", "fc1.bias"), ("fc2_w", "fc2.weight"), ("fc2_b", "fc2.bias")):
+            t = g(key); keep.append(t)
+            setattr(p, field, t.data_ptr())
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_engine_load_params(self.handle, ctypes.byref(p), ctypes.c_void_p(st)),
+                        "vs_engine_load_params")
+            torch.cuda.current_stream().synchronize()  # staging copies in `keep` may now be released
+
+    # ---- workspace ----------------------------------------------------------------------------
+    def _workspace(self, B, T, prec):
+        need = int(self.lib.vs_workspace_bytes(self.handle, B, T, prec))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    @staticmethod
+    def _prec(precision):
+        return _cabi.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+
+    def _check_inputs(self, x, emb):
+        if x.dim() != 3 or x.shape[2] != self.dims["num_freq"]:
+            raise ValueError(f"x must be [B, T, {self.dims['num_freq']}], got {tuple(x.shape)}")
+        if emb.dim() != 2 or emb.shape[0] != x.shape[0] or emb.shape[1] != self.dims["emb_dim"]:
+            raise ValueError(f"speaker_embedding must be [B, {self.dims['emb_dim']}], got {tuple(emb.shape)}")
+        if not x.is_cuda or not emb.is_cuda:
+            raise RuntimeError("inputs must be CUDA tensors (no CPU fallback)")
+
+    # ---- hot path -----------------------------------------------------------------------------
+    def forward(self, x, emb, precision="bf16x3", want_masked=False):
+        self._check_inputs(x, emb)
+        x = x.detach().to(torch.float32).contiguous()
+        emb = emb.detach().to(torch.float32).contiguous()
+        B, T, _ = x.shape
+        prec = self._prec(precision)
+        with torch.cuda.device(x.device):
+            ws, need = self._workspace(B, T, prec)
+            mask = torch.empty_like(x)
+            masked = torch.empty_like(x) if want_masked else None
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_forward(self.handle, _ptr(x), _ptr(emb), _ptr(mask), _ptr(masked), B, T, prec,
+                                            _ptr(ws), need, ctypes.c_void_p(st)), "vs_forward")
+        return (mask, masked) if want_masked else mask
+
+    def forward_host(self, x_host, emb_host, mask_host, masked_host=None, precision="bf16x3"):
+        """HOST tensors in, host tensors out (the end-to-end plugin call): H2D, forward, D2H, sync."""
+        B, T, _ = x_host.shape
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_forward_host(self.handle, _ptr(x_host), _ptr(emb_host), _ptr(mask_host),
+                                                 _ptr(masked_host), B, T, self._prec(precision), ctypes.c_void_p(st)),
+                        "vs_forward_host")
+        return mask_host
+
+    def conv_stack(self, x, precision="bf16x3"):
+        x = x.detach().to(torch.float32).contiguous()
+        B, T, F = x.shape
+        prec = self._prec(precision)
+        with torch.cuda.device(x.device):
+            ws, need = self._workspace(B, T, prec)
+            out = torch.empty(B, T, 8 * F, dtype=torch.float32, device=x.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_conv_stack(self.handle, _ptr(x), _ptr(out), B, T, prec, _ptr(ws), need,
+                                               ctypes.c_void_p(st)), "vs_conv_stack")
+        return out
+
+    # ---- test hooks ---------------------------------------------------------------------------
+    def debug_conv_layer(self, layer, inp, precision="fp32"):
+        inp = inp.detach().to(torch.float32).contiguous()
+        B, T = inp.shape[0], inp.shape[-2]
+        out = torch.empty(B, 64, T, self.dims["num_freq"], dtype=torch.float32, device=inp.device)
+        with torch.cuda.device(inp.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_debug_conv_layer(self.handle, layer, _ptr(inp), _ptr(out), B, T,
+                                                     self._prec(precision), ctypes.c_void_p(st)), "vs_debug_conv_layer")
+        return out
+
+    def debug_lstm_head(self, conv_out, emb, x, precision="fp32"):
+        conv_out = conv_out.detach().to(torch.float32).contiguous()
+        B, T, _ = conv_out.shape
+        lstm_out = torch.empty(B, T, 2 * self.dims["lstm_dim"], dtype=torch.float32, device=conv_out.device)
+        mask = torch.empty(B, T, self.dims["num_freq"], dtype=torch.float32, device=conv_out.device)
+        with torch.cuda.device(conv_out.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_debug_lstm_head(self.handle, _ptr(conv_out), _ptr(emb.contiguous()),
+                                                    _ptr(x.contiguous()), _ptr(lstm_out), _ptr(mask), B, T,
+                                                    self._prec(precision), ctypes.c_void_p(st)), "vs_debug_lstm_head")
+        return lstm_out, mask
+
+    def last_launch_count(self):
+        return int(self.lib.vs_last_launch_count(self.handle))
+
+    KERNEL_NAMES = {0: "cnn1", 1: "cnn2", 2: "cnn3", 3: "cnn4", 4: "cnn5", 5: "cnn6", 6: "cnn7", 7: "cnn8_reshape",
+                    8: "dvector_gate_bias", 9: "lstm_input_proj", 10: "lstm_recurrence", 11: "fc1", 12: "fc2_sigmoid_mask",
+                    13: "convert", 14: "head"}
+
+    def set_profiling(self, on):
+        _cabi.check(self.lib.vs_engine_set_profiling(self.handle, 1 if on else 0), "vs_engine_set_profiling")
+
+    def profile_read(self):
+        """[(kernel name, milliseconds)] of the last forward (profiling must be enabled)."""
+        ids = (ctypes.c_int32 * 64)()
+        ms = (ctypes.c_float * 64)()
+        n = self.lib.vs_profile_read(self.handle, 64, ids, ms)
+        return [(self.KERNEL_NAMES.get(ids[i], str(ids[i])), float(ms[i])) for i in range(n)]
