@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VOICESPLIT_PRECISION", "bf16x3"))
+    ap.add_argument("--precision", default=os.environ.get("VOICESPLIT_PRECISION", "fp16x3"))
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=601)
     ap.add_argument("--freq", type=int, default=257)
@@ -236,7 +236,7 @@ def main():
         if all(v is not None for v in conv_ms):
             avg = float(np.mean(conv_ms))
             ach = fl["conv5x5_layer"] * B / (avg / 1e3) / 1e12
-            passes = {"bf16x3": 3, "bf16": 1}.get(prec)
+            passes = {"bf16x3": 3, "fp16x3": 3, "bf16": 1, "fp16": 1}.get(prec)
             peak = peaks["bf16_tflops_sustained"]
             roof = {"bound": "tensor", "kernel": "dilated 5x5 conv 64->64 + BN + act (cnn3..cnn7)", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
@@ -246,7 +246,9 @@ def main():
         line = {"metric": "utterances/s (601-frame, 257-bin spectrogram) masked", "value": value, "unit": "utterances/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[prec],
+                "dtype": {"bf16x3": "bf16x3 (split-bf16 operands hi+lo, 3 MMAs, fp32 accumulate)",
+                          "fp16x3": "fp16x3 (split-fp16 operands hi+lo, 3 MMAs, fp32 accumulate)",
+                          "bf16": "bf16", "fp16": "f16", "fp32": "f32"}[prec],
                 "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "utterances/s", "ms_per_step": e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(xh.numel() * 4 + eh.numel() * 4),

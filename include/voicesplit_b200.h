@@ -47,6 +47,12 @@ extern "C" {
 #define VS_PREC_FP32 0
 #define VS_PREC_BF16X3 1
 #define VS_PREC_BF16 2
+/*   FP16X3 / FP16: the same two schemes with IEEE half operands (11-bit significand instead of 8):
+ *           hi + lo carries ~22 bits, i.e. fp32-grade products.  Half has a narrow exponent, so
+ *           weights are pre-scaled by a per-layer power of two (undone exactly in the epilogue) and
+ *           activations are clamped to +-60000 before conversion. */
+#define VS_PREC_FP16X3 3
+#define VS_PREC_FP16 4
 
 typedef struct vs_engine vs_engine;
 

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libvoicesplit_sm100.so")
 
 VS_OK = 0
 ACT_MISH, ACT_RELU = 0, 1
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3, PREC_FP16 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3, "fp16": PREC_FP16}
 
 _fp = ctypes.POINTER(ctypes.c_float)
 

@@ -124,7 +124,7 @@ static int check_common(const vs_engine* e, int B, int T, int precision) {
     if (!e) { set_error("null engine"); return VS_ERR_INVALID; }
     if (!e->loaded) { set_error("parameters not loaded: call vs_engine_load_params first"); return VS_ERR_STATE; }
     if (B < 1 || T < 1) { set_error("B and T must be >= 1"); return VS_ERR_INVALID; }
-    if (precision != VS_PREC_FP32 && precision != VS_PREC_BF16X3 && precision != VS_PREC_BF16) {
+    if (precision < VS_PREC_FP32 || precision > VS_PREC_FP16) {
         set_error("unknown precision"); return VS_ERR_INVALID;
     }
     if ((long long)B * T * padded_freq(e->d.num_freq) >= (1LL << 31) / 64) {

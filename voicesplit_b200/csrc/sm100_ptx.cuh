@@ -133,10 +133,10 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // Instruction descriptor for kind::f16: bf16 A/B (both K-major), fp32 D, shape M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int fp16 = 0) {
     return (1u << 4)                      // c_format  = F32
-           | (1u << 7)                    // a_format  = BF16
-           | (1u << 10)                   // b_format  = BF16
+           | ((fp16 ? 0u : 1u) << 7)      // a_format  = BF16 (1) or F16 (0)
+           | ((fp16 ? 0u : 1u) << 10)     // b_format
            | (0u << 15) | (0u << 16)      // a_major = b_major = K
            | ((uint32_t)(N >> 3) << 17)   // n_dim
            | ((uint32_t)(M >> 4) << 24);  // m_dim
@@ -171,7 +171,7 @@ inline PFN_tmapEncodeTiled get_tmap_encode() {
     }
     return fn;
 }
-// rank-`rank` bf16 tensor; dims/strides innermost first, strides[i] = byte stride of dim i+1
+// rank-`rank` tensor of 16-bit elements (bf16 or fp16: TMA only moves the bits); dims/strides innermost first, strides[i] = byte stride of dim i+1
 inline bool make_tmap_bf16(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box, CUtensorMapSwizzle swz) {
     PFN_tmapEncodeTiled enc = get_tmap_encode();
@@ -180,7 +180,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, void* base, int rank, const uint64_
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }

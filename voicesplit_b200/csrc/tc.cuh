@@ -4,6 +4,11 @@
 
 namespace vs {
 
+// precision -> (number of MMA passes, 16-bit element type: 0 = bf16, 1 = fp16)
+inline int tc_passes(int precision) { return (precision == VS_PREC_BF16X3 || precision == VS_PREC_FP16X3) ? 3 : 1; }
+inline int tc_elt(int precision) { return (precision == VS_PREC_FP16X3 || precision == VS_PREC_FP16) ? 1 : 0; }
+typedef unsigned short elt16;  // raw bits of a bf16 or fp16 value
+
 struct TcLstmBuffers {  // recurrent-kernel buffers shared with the fp32 path (carved by engine.cu)
     float* gates;       // [B*T][8H]
     float* bias_u;      // [B][8H]
@@ -24,5 +29,16 @@ int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_i
                    int precision, cudaStream_t st);
 int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, const float* x, float* mask, int B, int T,
                        int precision, const TcLstmBuffers& lb, cudaStream_t st);
+
+// ---- tc_gemm.cu: LSTM input projection / recurrence / FC head of the tensor-core path ------------
+int tc_gemm_pack(vs_engine* e, cudaStream_t st);
+size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision);
+// Everything after the 64-channel conv planes: cnn8 (+reshape), LSTM, head.  If conv_out32 is given
+// the planes are ignored and the LSTM input is taken from it (debug hook).
+int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32,
+                 const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, float* xcat32,
+                 float* fc1, void* gemm_ws, const TcLstmBuffers& lb, cudaStream_t st);
+cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
+                             elt16* xlo, int ldx, int B, int T, cudaStream_t st);
 
 }  // namespace vs

@@ -1,0 +1,617 @@
+// Tensor-core conv stack: cnn2..cnn7 as a tcgen05 implicit GEMM, plus the CUDA-core cnn1 / cnn8
+// kernels that feed and drain the bf16 activation planes.
+//
+// Data layout.  Activation planes are channels-last bf16 [B][Q][64] with Q = T*Fp flattened
+// pixels per utterance (Fp = padded_freq(F); pixels f >= F of every row are zero), stored as a
+// `hi` plane and - in the fp32-faithful BF16X3 mode - a `lo` plane with x ~= hi + lo.
+// A +-2 shift along F is a +-2 shift of the flat pixel index (it lands in the zero pad), a shift of
+// dt rows along T is a shift of dt*Fp, and anything outside [0, Q) is zero-filled by TMA, which
+// together are the reference's ZeroPad2d (models/voicesplit/model.py:16-47).
+//
+// GEMM mapping (per CTA tile of N consecutive flat pixels):
+//     D[128][N] (TMEM, fp32) += A[128][64] (weights, smem) * B[N][64]^T (pixels, smem)
+// A row 2*co+h holds tap (dt, df = 2j+h) of output channel co: one MMA applies TWO filter taps
+// to the same N input pixels (M = 128 keeps the tensor pipe at full rate although the layer has
+// only 64 output channels).  The two halves belong to output pixels one apart, so the epilogue
+// forms out[co][p] = D[2co][p] + D[2co+1][p+1] with one warp shuffle (adjacent lanes).
+// B is an N-row window into a strip of N+8 pixel rows that TMA loaded once per (dt, plane): the
+// five df taps reuse the strip by moving the window start (row-shifted 128B-swizzle descriptor).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+// (TMEM -> registers -> BN-fold + activation -> bf16 hi/lo -> global).  Two TMEM accumulators of
+// N columns double-buffer MMA against the epilogue; the CTA is persistent over tiles.
+#include "tc.cuh"
+#include "sm100_ptx.cuh"
+#include <cuda_fp16.h>
+
+namespace vs {
+using namespace ptx;
+
+constexpr int kWStages = 5;             // weight tiles (16 KB each) in flight
+constexpr int kWTileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct ConvTcArgs {
+    int Q, F, Fp, B;
+    int N;                // MMA N (pixels per tile incl. the one lost to the pair shift)
+    int tiles_per_utt, total_tiles;
+    int n_dt, n_j, halo;  // taps along T, tap pairs along F, strip halo (2 for 5x5, 0 for 7x1)
+    int dt_stride;        // dilation * Fp: flat-pixel offset of one tap step along T
+    int passes;           // 1 (bf16) or 3 (bf16x3)
+    int strip_rows, box_rows, n_boxes, s_stages;
+    int act;
+    const float* scale;
+    const float* shift;
+    elt16* out_hi;
+    elt16* out_lo;  // may be null (single-pass modes)
+};
+
+// 16-bit element conversion: ELT 0 = bf16, 1 = fp16 (clamped: half overflows at 65504)
+template <int ELT>
+__device__ __forceinline__ void split16(float y, elt16& hi, elt16& lo) {
+    if (ELT == 0) {
+        __nv_bfloat16 h = __float2bfloat16(y);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16(y - __bfloat162float(h)));
+    } else {
+        y = fminf(fmaxf(y, -60000.f), 60000.f);
+        __half h = __float2half_rn(y);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(y - __half2float(h)));
+    }
+}
+__device__ __forceinline__ void split16_rt(float y, int elt, elt16& hi, elt16& lo) {
+    if (elt == 0) split16<0>(y, hi, lo); else split16<1>(y, hi, lo);
+}
+__device__ __forceinline__ float join16(elt16 hi, elt16 lo, int elt) {
+    return elt == 0 ? __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo))
+                    : __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+    if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
+    return mish_f(x);
+}
+
+template <int ACT, int ELT>
+__global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
+                                                    const __grid_constant__ CUtensorMap tm_in_lo,
+                                                    const __grid_constant__ CUtensorMap tm_w_hi,
+                                                    const __grid_constant__ CUtensorMap tm_w_lo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int strip_bytes = a.strip_rows * 128;
+    uint8_t* w_ring = smem;
+    uint8_t* s_ring = smem + kWStages * kWTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)a.s_stages * strip_bytes);
+    uint64_t* w_full = bars;               // [kWStages]
+    uint64_t* w_empty = bars + kWStages;   // [kWStages]
+    uint64_t* s_full = bars + 2 * kWStages;             // [s_stages]
+    uint64_t* s_empty = s_full + a.s_stages;            // [s_stages]
+    uint64_t* acc_full = s_empty + a.s_stages;          // [2]
+    uint64_t* acc_empty = acc_full + 2;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < a.s_stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (lane == 0) {
+            prefetch_tensormap(&tm_in_hi); prefetch_tensormap(&tm_w_hi);
+            if (a.passes == 3) { prefetch_tensormap(&tm_in_lo); prefetch_tensormap(&tm_w_lo); }
+        }
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int useful = a.N - 1;
+    // per (dt): which (weight plane, strip plane) passes run.  bf16x3 = hi*hi + lo*hi + hi*lo,
+    // ordered so the hi strip is loaded once for the first two.
+    const int n_strip_loads = a.passes == 3 ? 2 : 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int ws = 0, wph = 0, ss = 0, sph = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_utt;
+                const int q0 = (tile - b * a.tiles_per_utt) * useful;
+                for (int dt = 0; dt < a.n_dt; ++dt) {
+                    const int qs = q0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
+                    for (int sp = 0; sp < n_strip_loads; ++sp) {  // strip plane: 0 = hi, 1 = lo
+                        mbar_wait(&s_empty[ss], sph ^ 1);
+                        mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
+                        uint8_t* dst = s_ring + (size_t)ss * strip_bytes;
+                        for (int i = 0; i < a.n_boxes; ++i)
+                            tma_load_3d(dst + (size_t)i * a.box_rows * 128, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[ss], 0,
+                                        qs + i * a.box_rows, b);
+                        if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
+                        // weight planes used against this strip: hi strip -> W hi (, W lo); lo strip -> W hi
+                        const int n_wp = (a.passes == 3 && sp == 0) ? 2 : 1;
+                        for (int wp = 0; wp < n_wp; ++wp) {
+                            for (int j = 0; j < a.n_j; ++j) {
+                                mbar_wait(&w_empty[ws], wph ^ 1);
+                                mbar_arrive_expect_tx(&w_full[ws], kWTileBytes);
+                                tma_load_2d(w_ring + (size_t)ws * kWTileBytes, wp == 0 ? &tm_w_hi : &tm_w_lo, &w_full[ws], 0,
+                                            (dt * a.n_j + j) * 128);
+                                if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = make_idesc_bf16(128, a.N, ELT);
+            int ws = 0, wph = 0, ss = 0, sph = 0, it = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * a.N);
+                uint32_t accumulate = 0;
+                for (int dt = 0; dt < a.n_dt; ++dt) {
+                    for (int sp = 0; sp < n_strip_loads; ++sp) {
+                        mbar_wait(&s_full[ss], sph);
+                        tc_fence_after();
+                        const uint32_t s_addr = smem_u32(s_ring + (size_t)ss * strip_bytes);
+                        const int n_wp = (a.passes == 3 && sp == 0) ? 2 : 1;
+                        for (int wp = 0; wp < n_wp; ++wp) {
+                            for (int j = 0; j < a.n_j; ++j) {
+                                mbar_wait(&w_full[ws], wph);
+                                tc_fence_after();
+                                const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWTileBytes);
+                                const uint32_t b_addr = s_addr + (uint32_t)(2 * j) * 128;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
+                                              idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                umma_commit(&w_empty[ws]);
+                                if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                            }
+                        }
+                        umma_commit(&s_empty[ss]);
+                        if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
+                    }
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int co = quad * 16 + (lane >> 1), h = lane & 1;
+        const float sc = a.scale[co], sh = a.shift[co];
+        const bool want_lo = a.out_lo != nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1, aph = (it >> 1) & 1;
+            const int b = tile / a.tiles_per_utt;
+            const int q0 = (tile - b * a.tiles_per_utt) * useful;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
+            int f = (q0 + h) % a.Fp;                     // frequency index of this lane's first pixel
+            elt16* ohi = a.out_hi + ((size_t)b * a.Q + q0) * 64 + co;
+            elt16* olo = want_lo ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
+            for (int c0 = 0; c0 < a.N; c0 += 32) {
+                uint32_t r[32];
+                uint32_t nxt = 0;
+                tmem_ld_32x32(t_base + c0, r);
+                if (c0 + 32 < a.N)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(nxt) : "r"(t_base + c0 + 32) : "memory");
+                tmem_ld_wait();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    // even lane (h=0, lower tap) owns pixel c0+2m, odd lane (upper tap) pixel c0+2m+1
+                    const float mine_odd = __uint_as_float(r[2 * m + 1]);
+                    const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
+                    const float up_next = __uint_as_float(m < 15 ? r[(2 * m + 2) & 31] : nxt);
+                    const float acc = h == 0 ? __uint_as_float(r[2 * m]) + other_odd : other_odd + up_next;
+                    const int p = c0 + 2 * m + h;
+                    if (p < useful && q0 + p < a.Q) {
+                        float y = (f < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
+                        elt16 yh, yl;
+                        split16<ELT>(y, yh, yl);
+                        ohi[(size_t)p * 64] = yh;
+                        if (want_lo) olo[(size_t)p * 64] = yl;
+                    }
+                    f += 2;
+                    if (f >= a.Fp) f -= a.Fp;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cnn1 on CUDA cores, writing the bf16 hi/lo planes (K = 7, C_in = 1: not MMA-shaped)
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(256) k_front_tc(const float* __restrict__ x, elt16* __restrict__ hi,
+                                                  elt16* __restrict__ lo, const float* __restrict__ w,
+                                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                                  int T, int F, int Fp, int elt) {
+    __shared__ float xs[32 + 6];
+    __shared__ float ws[7 * 64];
+    __shared__ float sc[64], sh[64];
+    const int f0 = blockIdx.x * 32, t = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+    const float* xrow = x + ((size_t)b * T + t) * F;
+    if (tid < 38) {
+        int f = f0 + tid - 3;
+        xs[tid] = (f >= 0 && f < F) ? xrow[f] : 0.f;
+    }
+    for (int i = tid; i < 7 * 64; i += 256) ws[i] = w[i];
+    if (tid < 64) { sc[tid] = scale[tid]; sh[tid] = shift[tid]; }
+    __syncthreads();
+    const int px = tid >> 3, cg = tid & 7, f = f0 + px;
+    if (f >= Fp) return;
+    __align__(16) elt16 vh[8], vl[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        int co = cg * 8 + c;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc = fmaf(ws[j * 64 + co], xs[px + j], acc);
+        float y = (f < F) ? activate<ACT>(fmaf(acc, sc[co], sh[co])) : 0.f;
+        split16_rt(y, elt, vh[c], vl[c]);
+    }
+    size_t o = (((size_t)b * T + t) * Fp + f) * 64 + cg * 8;
+    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(vh);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(vl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cnn8 (64 -> 8, 1x1) + BN + act from the bf16 planes; output row layout [B*T][ldx] with column
+// c*F+f, as fp32 and/or bf16 hi/lo (the LSTM input-projection operand)
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi, const elt16* __restrict__ lo, int elt,
+                                                   const float* __restrict__ w, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, float* __restrict__ x32,
+                                                   elt16* __restrict__ xhi, elt16* __restrict__ xlo, int ldx,
+                                                   int F, int Fp, long long npix) {
+    __shared__ float ws[64 * 8];
+    __shared__ float sc[8], sh[8];
+    for (int i = threadIdx.x; i < 512; i += 256) ws[i] = w[i];
+    if (threadIdx.x < 8) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+    long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (p >= npix) return;
+    int f = (int)(p % F);
+    long long bt = p / F;
+    const uint4* sh4 = reinterpret_cast<const uint4*>(hi + ((size_t)bt * Fp + f) * 64);
+    const uint4* sl4 = lo ? reinterpret_cast<const uint4*>(lo + ((size_t)bt * Fp + f) * 64) : nullptr;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 2
+    for (int q = 0; q < 8; ++q) {
+        uint4 vh = sh4[q];
+        uint4 vl = sl4 ? sl4[q] : make_uint4(0, 0, 0, 0);
+        const elt16* ph = reinterpret_cast<const elt16*>(&vh);
+        const elt16* pl = reinterpret_cast<const elt16*>(&vl);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = join16(ph[k], pl[k], elt);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, ws[(q * 8 + k) * 8 + c], acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float y = activate<ACT>(fmaf(acc[c], sc[c], sh[c]));
+        size_t o = (size_t)bt * ldx + (size_t)c * F + f;
+        if (x32) x32[o] = y;
+        if (xhi) {
+            elt16 yh, yl;
+            split16_rt(y, elt, yh, yl);
+            xhi[o] = yh;
+            if (xlo) xlo[o] = yl;
+        }
+    }
+}
+
+// fp32 plane [B][T][Fp][64] <-> bf16 hi/lo planes (debug hook)
+__global__ void k_plane_split(const float* __restrict__ p, elt16* __restrict__ hi, elt16* __restrict__ lo, int elt, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    elt16 h, l;
+    split16_rt(p[i], elt, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+}
+__global__ void k_plane_join(const elt16* __restrict__ hi, const elt16* __restrict__ lo, int elt, float* __restrict__ p, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p[i] = join16(hi[i], lo ? lo[i] : (elt16)0, elt);
+}
+
+// max |w| of a weight tensor (bits of a non-negative float order like unsigned ints)
+__global__ void k_absmax(const float* __restrict__ w, int n, unsigned int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicMax(out, __float_as_uint(fabsf(w[i])));
+}
+// power of two s with max|w| * s in [2^8, 2^9): keeps the `lo` halves of fp16 weights normal
+__device__ __forceinline__ float pow2_scale(unsigned int maxbits) {
+    float m = __uint_as_float(maxbits);
+    if (!(m > 0.f) || !isfinite(m)) return 1.f;
+    int ex;
+    frexpf(m, &ex);  // m = f * 2^ex, f in [0.5, 1)
+    return exp2f((float)(9 - ex));
+}
+// weights [tap][ci][co] fp32 -> tap-pair tiles [step][row = 2co+h][ci], scaled by s, as bf16 and fp16 hi / lo
+__global__ void k_pack_conv_tc(const float* __restrict__ w32, const unsigned int* __restrict__ maxbits, elt16* __restrict__ bhi,
+                               elt16* __restrict__ blo, elt16* __restrict__ hhi, elt16* __restrict__ hlo, int kh, int kw, int n_j) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = kh * n_j * 128 * 64;
+    if (i >= n) return;
+    const float s = pow2_scale(*maxbits);
+    int ci = i & 63, row = (i >> 6) & 127, step = i >> 13;
+    int dt = step / n_j, j = step % n_j;
+    int co = row >> 1, h = row & 1, df = 2 * j + h;
+    float v = (df < kw) ? s * w32[((size_t)(dt * kw + df) * 64 + ci) * 64 + co] : 0.f;
+    split16<0>(v, bhi[i], blo[i]);
+    split16<1>(v, hhi[i], hlo[i]);
+}
+__global__ void k_scale_tc(const float* __restrict__ scale, const unsigned int* __restrict__ maxbits, float* __restrict__ out, int n) {
+    int i = threadIdx.x;
+    if (i < n) out[i] = scale[i] / pow2_scale(*maxbits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TcState {
+    elt16* w_hi[2][8] = {};   // [elt][layer]
+    elt16* w_lo[2][8] = {};
+    float* scale_tc[8] = {};  // BN scale divided by the layer's power-of-two weight scale
+    unsigned int* wmax = nullptr;
+    int max_smem = 0;
+};
+
+static int tile_n_for(const vs_engine*) { return 256; }
+
+int tc_create(vs_engine* e) {
+    TcState* s = new TcState();
+    e->tc = s;
+    cudaDeviceGetAttribute(&s->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+    return VS_OK;
+}
+void tc_destroy(vs_engine* e) {
+    TcState* s = (TcState*)e->tc;
+    if (!s) return;
+    for (int l = 0; l < 8; ++l) {
+        for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); }
+        cudaFree(s->scale_tc[l]);
+    }
+    cudaFree(s->wmax);
+    delete s;
+    e->tc = nullptr;
+}
+
+int tc_pack(vs_engine* e, cudaStream_t st) {
+    TcState* s = (TcState*)e->tc;
+    if (!s->wmax) VS_CUDA_TRY(cudaMalloc(&s->wmax, 8 * sizeof(unsigned int)));
+    VS_CUDA_TRY(cudaMemsetAsync(s->wmax, 0, 8 * sizeof(unsigned int), st));
+    for (int l = 1; l <= 6; ++l) {
+        const ConvGeom g = kConv[l];
+        const int n_j = (g.kw + 1) / 2;
+        const size_t n = (size_t)g.kh * n_j * 128 * 64;
+        if (!s->w_hi[0][l]) {
+            for (int t = 0; t < 2; ++t) {
+                VS_CUDA_TRY(cudaMalloc(&s->w_hi[t][l], n * sizeof(elt16)));
+                VS_CUDA_TRY(cudaMalloc(&s->w_lo[t][l], n * sizeof(elt16)));
+            }
+            VS_CUDA_TRY(cudaMalloc(&s->scale_tc[l], 64 * sizeof(float)));
+        }
+        const int nw = g.cout * g.cin * g.kh * g.kw;
+        k_absmax<<<(nw + 255) / 256, 256, 0, st>>>(e->conv_w32[l], nw, s->wmax + l);
+        k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_hi[0][l], s->w_lo[0][l],
+                                                                    s->w_hi[1][l], s->w_lo[1][l], g.kh, g.kw, n_j);
+        k_scale_tc<<<1, 64, 0, st>>>(e->conv_scale[l], s->wmax + l, s->scale_tc[l], 64);
+    }
+    VS_CUDA_TRY(cudaGetLastError());
+    return tc_gemm_pack(e, st);
+}
+
+static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo,
+                          elt16* out_hi, elt16* out_lo, int B, int T, int precision, cudaStream_t st) {
+    TcState* s = (TcState*)e->tc;
+    const ConvGeom g = kConv[layer];
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    ConvTcArgs a{};
+    a.Q = T * Fp; a.F = F; a.Fp = Fp; a.B = B;
+    a.N = tile_n_for(e);
+    a.tiles_per_utt = (a.Q + a.N - 2) / (a.N - 1);
+    a.total_tiles = B * a.tiles_per_utt;
+    a.n_dt = g.kh; a.n_j = (g.kw + 1) / 2; a.halo = g.kw / 2;
+    a.dt_stride = g.dil * Fp;
+    a.passes = tc_passes(precision);
+    const int elt = tc_elt(precision);
+    a.strip_rows = a.N + 8;
+    a.box_rows = a.strip_rows;
+    a.n_boxes = 1;
+    while (a.box_rows > 256 || (a.box_rows % 8) != 0) {  // split the strip into equal boxes of a multiple of 8 rows
+        a.n_boxes++;
+        if (a.strip_rows % a.n_boxes) { a.box_rows = 1000; continue; }
+        a.box_rows = a.strip_rows / a.n_boxes;
+        if (a.n_boxes > 64) { set_error("cannot split strip into TMA boxes"); return VS_ERR_INVALID; }
+    }
+    a.act = e->d.activation;
+    a.scale = s->scale_tc[layer]; a.shift = e->conv_shift[layer];
+    a.out_hi = out_hi; a.out_lo = (a.passes == 3) ? out_lo : nullptr;
+    const int strip_bytes = a.strip_rows * 128;
+    const int fixed = 1024 + kWStages * kWTileBytes + 512;
+    a.s_stages = (s->max_smem - fixed) / strip_bytes;
+    if (a.s_stages > 6) a.s_stages = 6;
+    if (a.s_stages < 2) { set_error("not enough shared memory for the conv strips"); return VS_ERR_UNSUPPORTED; }
+    const int smem = fixed + a.s_stages * strip_bytes;
+
+    CUtensorMap tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo;
+    {
+        uint64_t dims[3] = {64, (uint64_t)a.Q, (uint64_t)B};
+        uint64_t str[2] = {128, (uint64_t)a.Q * 128};
+        uint32_t box[3] = {64, (uint32_t)a.box_rows, 1};
+        bool ok = make_tmap_bf16(&tm_in_hi, (void*)in_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_in_lo, (void*)(in_lo ? in_lo : in_hi), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        uint64_t wd[2] = {64, (uint64_t)a.n_dt * a.n_j * 128};
+        uint64_t ws[1] = {128};
+        uint32_t wb[2] = {64, 128};
+        ok = ok && make_tmap_bf16(&tm_w_hi, s->w_hi[elt][layer], 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_lo, s->w_lo[elt][layer], 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!ok) { set_error("cuTensorMapEncodeTiled failed"); return VS_ERR_CUDA; }
+    }
+    int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
+    cudaError_t ce;
+#define VS_CONV_TC(A, E)                                                                                  \
+    do {                                                                                                  \
+        ce = cudaFuncSetAttribute(k_conv_tc<A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
+        if (ce == cudaSuccess) k_conv_tc<A, E><<<grid, 192, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+    } while (0)
+    if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1); else VS_CONV_TC(VS_ACT_RELU, 0); }
+    else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1); else VS_CONV_TC(VS_ACT_MISH, 0); }
+#undef VS_CONV_TC
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) { set_error(std::string("k_conv_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
+    e->launches++;
+    if (e->profiling) prof_after(e, KID_CONV1 + layer - 1, st);
+    return VS_OK;
+}
+
+static cudaError_t launch_front_tc(const vs_engine* e, const float* x, elt16* hi, elt16* lo, int elt, int B, int T, cudaStream_t st) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    dim3 grid((Fp + 31) / 32, T, B);
+    if (e->d.activation == VS_ACT_RELU)
+        k_front_tc<VS_ACT_RELU><<<grid, 256, 0, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], T, F, Fp, elt);
+    else
+        k_front_tc<VS_ACT_MISH><<<grid, 256, 0, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], T, F, Fp, elt);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32,
+                                    elt16* xhi, elt16* xlo, int ldx, int B, int T, cudaStream_t st) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    long long npix = (long long)B * T * F;
+    unsigned grid = (unsigned)((npix + 255) / 256);
+    if (e->d.activation == VS_ACT_RELU)
+        k_point8_tc<VS_ACT_RELU><<<grid, 256, 0, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, npix);
+    else
+        k_point8_tc<VS_ACT_MISH><<<grid, 256, 0, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, npix);
+    return cudaGetLastError();
+}
+
+// ---- workspace of the tensor-core path ---------------------------------------------------------
+struct TcWorkspace {
+    elt16 *a_hi, *a_lo, *b_hi, *b_lo;  // ping-pong activation planes
+    float* xcat32;                              // [B*T][8F]
+    float* fc1;                                 // [B*T][fc1]
+    void* gemm;                                 // operands of the tensor-core GEMMs
+    size_t total;
+};
+static TcWorkspace tc_carve(const vs_engine* e, int B, int T, int precision, void* base) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 1024); return r; };
+    const size_t plane = (size_t)B * T * Fp * 64 * sizeof(elt16);
+    TcWorkspace w{};
+    w.a_hi = (elt16*)take(plane);
+    w.b_hi = (elt16*)take(plane);
+    if (tc_passes(precision) == 3) {
+        w.a_lo = (elt16*)take(plane);
+        w.b_lo = (elt16*)take(plane);
+    }
+    w.xcat32 = (float*)take((size_t)B * T * 8 * F * sizeof(float));
+    w.fc1 = (float*)take((size_t)B * T * e->d.fc1_dim * sizeof(float));
+    w.gemm = take(tc_gemm_workspace_bytes(e, B, T, precision));
+    w.total = off;
+    return w;
+}
+size_t tc_workspace_bytes(const vs_engine* e, int B, int T, int precision) { return tc_carve(e, B, T, precision, nullptr).total; }
+
+// conv stack on tensor cores; result in the bf16 plane pair returned through (*res_hi, *res_lo)
+static int conv_layers_tc(vs_engine* e, const float* x, const TcWorkspace& w, int B, int T, int precision, cudaStream_t st,
+                          elt16** res_hi, elt16** res_lo) {
+    VS_LAUNCH(e, KID_FRONT, st, launch_front_tc(e, x, w.a_hi, w.a_lo, tc_elt(precision), B, T, st));
+    elt16 *sh = w.a_hi, *sl = w.a_lo, *dh = w.b_hi, *dl = w.b_lo;
+    for (int l = 1; l <= 6; ++l) {
+        int rc = launch_conv_tc(e, l, sh, sl, dh, dl, B, T, precision, st);
+        if (rc != VS_OK) return rc;
+        elt16* t;
+        t = sh; sh = dh; dh = t;
+        t = sl; sl = dl; dl = t;
+    }
+    *res_hi = sh; *res_lo = sl;
+    return VS_OK;
+}
+
+int tc_conv_stack(vs_engine* e, const float* x, float* conv_out, int B, int T, int precision, void* ws, cudaStream_t st) {
+    TcWorkspace w = tc_carve(e, B, T, precision, ws);
+    elt16 *rh, *rl;
+    int rc = conv_layers_tc(e, x, w, B, T, precision, st, &rh, &rl);
+    if (rc != VS_OK) return rc;
+    VS_LAUNCH(e, KID_POINT8, st, launch_point8_tc(e, rh, rl, tc_elt(precision), conv_out, nullptr, nullptr, 8 * e->d.num_freq, B, T, st));
+    return VS_OK;
+}
+
+int tc_forward(vs_engine* e, const float* x, const float* emb, float* mask, float* masked, int B, int T, int precision,
+               void* ws, const TcLstmBuffers& lb, cudaStream_t st) {
+    TcWorkspace w = tc_carve(e, B, T, precision, ws);
+    elt16 *rh, *rl;
+    int rc = conv_layers_tc(e, x, w, B, T, precision, st, &rh, &rl);
+    if (rc != VS_OK) return rc;
+    return tc_lstm_head(e, rh, rl, nullptr, emb, x, mask, masked, B, T, precision, w.xcat32, w.fc1, w.gemm, lb, st);
+}
+
+int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_in, float* plane_out, int B, int T,
+                   int precision, cudaStream_t st) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    const long long n = (long long)B * T * Fp * 64;
+    elt16* buf = nullptr;
+    VS_CUDA_TRY(cudaMalloc(&buf, (size_t)n * 4 * sizeof(elt16)));
+    elt16 *ih = buf, *il = buf + n, *oh = buf + 2 * n, *ol = buf + 3 * n;
+    const bool x3 = tc_passes(precision) == 3;
+    const int elt = tc_elt(precision);
+    int rc = VS_OK;
+    cudaError_t ce = cudaSuccess;
+    if (layer == 0) {
+        ce = launch_front_tc(e, x, oh, x3 ? ol : nullptr, elt, B, T, st);
+    } else {
+        k_plane_split<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(plane_in, ih, x3 ? il : nullptr, elt, n);
+        rc = launch_conv_tc(e, layer, ih, x3 ? il : nullptr, oh, ol, B, T, precision, st);
+    }
+    if (rc == VS_OK && ce == cudaSuccess) {
+        k_plane_join<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, x3 ? ol : nullptr, elt, plane_out, n);
+        ce = cudaStreamSynchronize(st);
+    }
+    cudaFree(buf);
+    if (ce != cudaSuccess) { set_error(std::string("tc_debug_layer: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
+    return rc;
+}
+
+cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
+                             elt16* xlo, int ldx, int B, int T, cudaStream_t st) {
+    return launch_point8_tc(e, hi, lo, elt, x32, xhi, xlo, ldx, B, T, st);
+}
+
+}  // namespace vs

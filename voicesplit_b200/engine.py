@@ -96,7 +96,7 @@ class MaskEngine:
             raise RuntimeError("inputs must be CUDA tensors (no CPU fallback)")
 
     # ---- hot path -----------------------------------------------------------------------------
-    def forward(self, x, emb, precision="bf16x3", want_masked=False):
+    def forward(self, x, emb, precision="fp16x3", want_masked=False):
         self._check_inputs(x, emb)
         x = x.detach().to(torch.float32).contiguous()
         emb = emb.detach().to(torch.float32).contiguous()
@@ -111,7 +111,7 @@ class MaskEngine:
                                             _ptr(ws), need, ctypes.c_void_p(st)), "vs_forward")
         return (mask, masked) if want_masked else mask
 
-    def forward_host(self, x_host, emb_host, mask_host, masked_host=None, precision="bf16x3"):
+    def forward_host(self, x_host, emb_host, mask_host, masked_host=None, precision="fp16x3"):
         """HOST tensors in, host tensors out (the end-to-end plugin call): H2D, forward, D2H, sync."""
         B, T, _ = x_host.shape
         with torch.cuda.device(self.device):
@@ -121,7 +121,7 @@ class MaskEngine:
                         "vs_forward_host")
         return mask_host
 
-    def conv_stack(self, x, precision="bf16x3"):
+    def conv_stack(self, x, precision="fp16x3"):
         x = x.detach().to(torch.float32).contiguous()
         B, T, F = x.shape
         prec = self._prec(precision)

@@ -67,9 +67,9 @@ class MaskEstimator(nn.Module):
                             batch_first=True, bidirectional=True)
         self.fc1 = nn.Linear(2 * self.dims["lstm_dim"], self.dims["fc1_dim"])
         self.fc2 = nn.Linear(self.dims["fc1_dim"], self.dims["fc2_dim"])
-        # arithmetic of the contractions: "bf16x3" (fp32-faithful split bf16 on tensor cores),
-        # "bf16" (fast) or "fp32" (CUDA cores); see include/voicesplit_b200.h
-        self.precision = os.environ.get("VOICESPLIT_PRECISION", "bf16x3")
+        # arithmetic of the contractions: "fp16x3" / "bf16x3" (fp32-faithful split operands on tensor
+        # cores), "fp16" / "bf16" (single pass, fast) or "fp32" (CUDA cores); see include/voicesplit_b200.h
+        self.precision = os.environ.get("VOICESPLIT_PRECISION", "fp16x3")
         self._engine = None
         self._packed_sig = None
 
