@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -44,6 +45,30 @@ __device__ __forceinline__ float activate(float x) {
     return mish_precise(x);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+typedef unsigned short elt16;  // raw bits of a bf16 or fp16 value
+// 16-bit element conversion: ELT 0 = bf16, 1 = fp16 (clamped: half overflows at 65504)
+template <int ELT>
+__device__ __forceinline__ void split16(float y, elt16& hi, elt16& lo) {
+    if (ELT == 0) {
+        __nv_bfloat16 h = __float2bfloat16(y);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16(y - __bfloat162float(h)));
+    } else {
+        y = fminf(fmaxf(y, -60000.f), 60000.f);
+        __half h = __float2half_rn(y);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(y - __half2float(h)));
+    }
+}
+__device__ __forceinline__ void split16_rt(float y, int elt, elt16& hi, elt16& lo) {
+    if (elt == 0) split16<0>(y, hi, lo); else split16<1>(y, hi, lo);
+}
+__device__ __forceinline__ float join16(elt16 hi, elt16 lo, int elt) {
+    return elt == 0 ? __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo))
+                    : __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
+}
+
 
 // ---- error plumbing ---------------------------------------------------------------------------
 void set_error(const std::string& msg);
@@ -119,8 +144,10 @@ enum GemmEpi { EPI_NONE = 0, EPI_RELU = 1, EPI_SIGMOID_MASK = 2 };
 cudaError_t launch_gemm_fp32(const float* A, int lda, const float* W, int ldw, const float* bias,
                              const float* bias_group, int group_rows, float* C, int ldc, int M, int N, int K,
                              bool relu_a, GemmEpi epi, const float* xmul, float* masked, cudaStream_t st);
+// hr_hi/hr_lo (optional): relu(h) as 16-bit hi/lo planes [B*T][2H] - the fc1 operand of the tensor-core head
 cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float* hout, float* hx,
-                                 unsigned int* barrier, int B, int T, cudaStream_t st);
+                                 unsigned int* barrier, int B, int T, cudaStream_t st, elt16* hr_hi = nullptr,
+                                 elt16* hr_lo = nullptr, int elt = 0);
 size_t lstm_rec_scratch_bytes(const vs_engine* e, int B);
 // layout converters for the debug hooks
 cudaError_t launch_nchw_to_plane(const float* nchw, float* plane, int B, int C, int T, int F, cudaStream_t st);

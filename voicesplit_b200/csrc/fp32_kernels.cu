@@ -291,7 +291,8 @@ __device__ __forceinline__ void dir_barrier(unsigned int* counter, unsigned int 
 __global__ void __launch_bounds__(256, 1) k_lstm_rec_fp32(const float* __restrict__ gates_x, const float* __restrict__ whh,
                                                           float* __restrict__ hout, float* hx, float* cstate,
                                                           unsigned int* barrier, unsigned int barrier_base,
-                                                          int B, int Bp, int T, int H, int nslices) {
+                                                          int B, int Bp, int T, int H, int nslices,
+                                                          elt16* __restrict__ hr_hi, elt16* __restrict__ hr_lo, int elt) {
     extern __shared__ __align__(16) float smem[];
     float* wt = smem;                  // [H][kHS][4]   (k, unit, gate)
     float* ht = smem + (size_t)H * 32; // [H][kBT]
@@ -356,7 +357,14 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec_fp32(const float* __restric
                     float h_new = og * tanhf(c_new);
                     *cp = c_new;
                     hnext[(size_t)hj * Bp + b] = h_new;
-                    hout[((size_t)b * T + t) * 2 * H + (size_t)d * H + hj] = h_new;
+                    const size_t oidx = ((size_t)b * T + t) * 2 * H + (size_t)d * H + hj;
+                    hout[oidx] = h_new;
+                    if (hr_hi) {
+                        elt16 vh, vl;
+                        split16_rt(fmaxf(h_new, 0.f), elt, vh, vl);
+                        hr_hi[oidx] = vh;
+                        if (hr_lo) hr_lo[oidx] = vl;
+                    }
                 }
             }
         }
@@ -371,10 +379,9 @@ size_t lstm_rec_scratch_bytes(const vs_engine* e, int B) {
     return (size_t)(4 + 2) * H * Bp * sizeof(float);
 }
 
-static unsigned int g_barrier_epoch = 0;  // counters are monotonic; each launch gets a fresh base
 
 cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float* hout, float* hx,
-                                 unsigned int* barrier, int B, int T, cudaStream_t st) {
+                                 unsigned int* barrier, int B, int T, cudaStream_t st, elt16* hr_hi, elt16* hr_lo, int elt) {
     const int H = e->d.lstm_dim;
     const int nslices = (H + kHS - 1) / kHS;
     const int Bp = (int)align_up((size_t)B, kBT);
@@ -387,11 +394,11 @@ cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float
     err = cudaMemsetAsync(barrier, 0, 2 * sizeof(unsigned int), st);
     if (err != cudaSuccess) return err;
     unsigned int base = 0;
-    (void)g_barrier_epoch;
     const float* whh = e->whh;
     int Bv = B, Bpv = Bp, Tv = T, Hv = H, ns = nslices;
     void* args[] = {(void*)&gates_x, (void*)&whh, (void*)&hout, (void*)&hx, (void*)&cstate, (void*)&barrier,
-                    (void*)&base, (void*)&Bv, (void*)&Bpv, (void*)&Tv, (void*)&Hv, (void*)&ns};
+                    (void*)&base, (void*)&Bv, (void*)&Bpv, (void*)&Tv, (void*)&Hv, (void*)&ns,
+                    (void*)&hr_hi, (void*)&hr_lo, (void*)&elt};
     return cudaLaunchCooperativeKernel((const void*)k_lstm_rec_fp32, dim3(2 * nslices), dim3(256), args, smem, st);
 }
 

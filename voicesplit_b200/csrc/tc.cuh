@@ -7,7 +7,6 @@ namespace vs {
 // precision -> (number of MMA passes, 16-bit element type: 0 = bf16, 1 = fp16)
 inline int tc_passes(int precision) { return (precision == VS_PREC_BF16X3 || precision == VS_PREC_FP16X3) ? 3 : 1; }
 inline int tc_elt(int precision) { return (precision == VS_PREC_FP16X3 || precision == VS_PREC_FP16) ? 1 : 0; }
-typedef unsigned short elt16;  // raw bits of a bf16 or fp16 value
 
 struct TcLstmBuffers {  // recurrent-kernel buffers shared with the fp32 path (carved by engine.cu)
     float* gates;       // [B*T][8H]
@@ -32,6 +31,7 @@ int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, co
 
 // ---- tc_gemm.cu: LSTM input projection / recurrence / FC head of the tensor-core path ------------
 int tc_gemm_pack(vs_engine* e, cudaStream_t st);
+void tc_gemm_destroy(vs_engine* e);
 size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision);
 // Everything after the 64-channel conv planes: cnn8 (+reshape), LSTM, head.  If conv_out32 is given
 // the planes are ignored and the LSTM input is taken from it (debug hook).

@@ -17,9 +17,11 @@
 // B is an N-row window into a strip of N+8 pixel rows that TMA loaded once per (dt, plane): the
 // five df taps reuse the strip by moving the window start (row-shifted 128B-swizzle descriptor).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
-// (TMEM -> registers -> BN-fold + activation -> bf16 hi/lo -> global).  Two TMEM accumulators of
-// N columns double-buffer MMA against the epilogue; the CTA is persistent over tiles.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-17 = epilogue
+// (TMEM -> registers -> BN-fold + activation -> 16-bit hi/lo -> global; four warps per TMEM lane
+// quadrant, each taking every fourth 32-column chunk, so every SM sub-partition has four warps to
+// hide the MUFU/shuffle latency of the Mish epilogue).  Two TMEM accumulators of N columns
+// double-buffer MMA against the epilogue; the CTA is persistent over tiles.
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
 #include <cuda_fp16.h>
@@ -28,6 +30,8 @@ namespace vs {
 using namespace ptx;
 
 constexpr int kWStages = 5;             // weight tiles (16 KB each) in flight
+constexpr int kEpiWarps = 16;           // epilogue warps (4 per TMEM lane quadrant)
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 constexpr int kWTileBytes = 128 * 128;  // 128 rows x 64 bf16
 
 struct ConvTcArgs {
@@ -45,28 +49,6 @@ struct ConvTcArgs {
     elt16* out_lo;  // may be null (single-pass modes)
 };
 
-// 16-bit element conversion: ELT 0 = bf16, 1 = fp16 (clamped: half overflows at 65504)
-template <int ELT>
-__device__ __forceinline__ void split16(float y, elt16& hi, elt16& lo) {
-    if (ELT == 0) {
-        __nv_bfloat16 h = __float2bfloat16(y);
-        hi = __bfloat16_as_ushort(h);
-        lo = __bfloat16_as_ushort(__float2bfloat16(y - __bfloat162float(h)));
-    } else {
-        y = fminf(fmaxf(y, -60000.f), 60000.f);
-        __half h = __float2half_rn(y);
-        hi = __half_as_ushort(h);
-        lo = __half_as_ushort(__float2half_rn(y - __half2float(h)));
-    }
-}
-__device__ __forceinline__ void split16_rt(float y, int elt, elt16& hi, elt16& lo) {
-    if (elt == 0) split16<0>(y, hi, lo); else split16<1>(y, hi, lo);
-}
-__device__ __forceinline__ float join16(elt16 hi, elt16 lo, int elt) {
-    return elt == 0 ? __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo))
-                    : __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
-}
-
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
     if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
@@ -74,7 +56,7 @@ __device__ __forceinline__ float act_fast(float x) {
 }
 
 template <int ACT, int ELT>
-__global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
                                                     const __grid_constant__ CUtensorMap tm_w_hi,
                                                     const __grid_constant__ CUtensorMap tm_w_lo) {
@@ -96,7 +78,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvTcArgs a, const __
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < a.s_stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -191,8 +173,9 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvTcArgs a, const __
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..17) =====================
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int cgrp = (warp - 2) >> 2;                // which 32-column chunks this warp takes
         const int co = quad * 16 + (lane >> 1), h = lane & 1;
         const float sc = a.scale[co], sh = a.shift[co];
         const bool want_lo = a.out_lo != nullptr;
@@ -204,10 +187,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvTcArgs a, const __
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
-            int f = (q0 + h) % a.Fp;                     // frequency index of this lane's first pixel
+            int f = (q0 + h + cgrp * 32) % a.Fp;         // frequency index of this lane's first pixel
             elt16* ohi = a.out_hi + ((size_t)b * a.Q + q0) * 64 + co;
             elt16* olo = want_lo ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
-            for (int c0 = 0; c0 < a.N; c0 += 32) {
+            for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (kEpiWarps / 4)) {
                 uint32_t r[32];
                 uint32_t nxt = 0;
                 tmem_ld_32x32(t_base + c0, r);
@@ -232,6 +215,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvTcArgs a, const __
                     f += 2;
                     if (f >= a.Fp) f -= a.Fp;
                 }
+                f = (f + 32 * (kEpiWarps / 4 - 1)) % a.Fp;   // skip the chunks the other warps take
             }
             tc_fence_before();
             __syncwarp();
@@ -382,6 +366,7 @@ __global__ void k_scale_tc(const float* __restrict__ scale, const unsigned int* 
 // host side
 // ---------------------------------------------------------------------------------------------
 struct TcState {
+    void* gemm = nullptr;     // GemmState of tc_gemm.cu (must stay the first member)
     elt16* w_hi[2][8] = {};   // [elt][layer]
     elt16* w_lo[2][8] = {};
     float* scale_tc[8] = {};  // BN scale divided by the layer's power-of-two weight scale
@@ -400,6 +385,7 @@ int tc_create(vs_engine* e) {
 void tc_destroy(vs_engine* e) {
     TcState* s = (TcState*)e->tc;
     if (!s) return;
+    tc_gemm_destroy(e);
     for (int l = 0; l < 8; ++l) {
         for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); }
         cudaFree(s->scale_tc[l]);
@@ -486,7 +472,7 @@ static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt
 #define VS_CONV_TC(A, E)                                                                                  \
     do {                                                                                                  \
         ce = cudaFuncSetAttribute(k_conv_tc<A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
-        if (ce == cudaSuccess) k_conv_tc<A, E><<<grid, 192, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+        if (ce == cudaSuccess) k_conv_tc<A, E><<<grid, kConvThreads, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
     if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1); else VS_CONV_TC(VS_ACT_RELU, 0); }
     else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1); else VS_CONV_TC(VS_ACT_MISH, 0); }

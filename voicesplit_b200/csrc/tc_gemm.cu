@@ -1,43 +1,398 @@
-// LSTM input projection, recurrence and FC head of the tensor-core precision modes.
-// v1: cnn8 writes the fp32 LSTM input and the contractions after the conv stack still run on the
-// fp32 CUDA-core kernels (fp32_kernels.cu); the tcgen05 GEMM replaces them next.
+// LSTM input projection and FC head on tensor cores: one warp-specialised tcgen05 GEMM
+//     C[M][N] = A[M][K] * W[N][K]^T      (A = activations, rows = (utterance, frame); W = weights)
+// with split 16-bit operands (hi/lo planes, 1 or 3 MMA passes into one fp32 TMEM accumulator) and
+// three fused epilogues:
+//   GATES : + per-utterance gate bias (W_ih[:,8F:] emb + b_ih + b_hh)  -> fp32 gates_x for the recurrence
+//   FC1   : + bias, ReLU                                               -> 16-bit hi/lo operand of fc2
+//   FC2   : + bias, sigmoid, * spectrogram                             -> mask (and masked) fp32
+// Tile: 128 rows of A (the MMA M, one TMEM lane per row) x n_tile <= 256 rows of W (the MMA N).
+// K is walked in 64-element blocks (one 128-byte swizzle atom per row); TMA zero-fills the K and
+// N tails, so nothing is padded in memory.  Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.
 #include "tc.cuh"
+#include "sm100_ptx.cuh"
 
 namespace vs {
+using namespace ptx;
 
-int tc_gemm_pack(vs_engine*, cudaStream_t) { return VS_OK; }
-size_t tc_gemm_workspace_bytes(const vs_engine*, int, int, int) { return 1024; }
+constexpr int kGemmStages = 4;
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
+enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2 };
 
-int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32,
-                 const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, float* xcat32,
-                 float* fc1, void*, const TcLstmBuffers& lb, cudaStream_t st) {
-    const int F = e->d.num_freq, H = e->d.lstm_dim, E = e->d.emb_dim, N1 = e->d.fc1_dim;
-    const int M = B * T;
-    const float* xin = conv_out32;
-    if (!xin) {
-        VS_LAUNCH(e, KID_POINT8, st, tc_launch_point8(e, plane_hi, plane_lo, tc_elt(precision), xcat32, nullptr, nullptr, 8 * F, B, T, st));
-        xin = xcat32;
+struct GemmTcArgs {
+    int M, N, K;
+    int lda, ldw;               // row strides (elements) of the 16-bit A and W planes, multiples of 8
+    int n_tile, n_tiles_n, n_tiles_m, total_tiles, n_kb;
+    int passes;
+    int group_rows;             // GATES: rows per utterance (T)
+    const float* bias;          // [N] (FC1/FC2) or null
+    const float* bias_group;    // [M / group_rows][N] (GATES)
+    float* out32;               // GATES: [M][N]; FC2: mask [M][N]
+    int ld_out;
+    elt16* out_hi;              // FC1: [M][ld16]
+    elt16* out_lo;
+    int ld16;
+    const float* xmul;          // FC2: spectrogram [M][N]
+    float* masked;              // FC2: optional
+};
+
+template <int EPI, int ELT>
+__global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a, const __grid_constant__ CUtensorMap tm_a_hi,
+                                                             const __grid_constant__ CUtensorMap tm_a_lo,
+                                                             const __grid_constant__ CUtensorMap tm_w_hi,
+                                                             const __grid_constant__ CUtensorMap tm_w_lo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = 128 * 128, w_bytes = a.n_tile * 128;
+    const int w_bytes_al = (w_bytes + 1023) & ~1023;
+    const int stage_bytes = a_bytes + w_bytes_al;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGemmStages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kGemmStages;
+    uint64_t* acc_full = empty + kGemmStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGemmEpiWarps); }
+        fence_barrier_init();
+        prefetch_tensormap(&tm_a_hi); prefetch_tensormap(&tm_w_hi);
     }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
+                for (int pass = 0; pass < a.passes; ++pass) {
+                    // pass 0: A_hi*W_hi, pass 1: A_lo*W_hi, pass 2: A_hi*W_lo
+                    const CUtensorMap* ta = pass == 1 ? &tm_a_lo : &tm_a_hi;
+                    const CUtensorMap* tw = pass == 2 ? &tm_w_lo : &tm_w_hi;
+                    for (int kb = 0; kb < a.n_kb; ++kb) {
+                        mbar_wait(&empty[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + w_bytes));
+                        uint8_t* dst = smem + (size_t)st * stage_bytes;
+                        tma_load_2d(dst, ta, &full[st], kb * 64, mb * 128);
+                        tma_load_2d(dst + a_bytes, tw, &full[st], kb * 64, nb * a.n_tile);
+                        if (++st == kGemmStages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, a.n_tile, ELT);
+            int st = 0, ph = 0, it = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * 256);
+                uint32_t accumulate = 0;
+                for (int pass = 0; pass < a.passes; ++pass) {
+                    for (int kb = 0; kb < a.n_kb; ++kb) {
+                        mbar_wait(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + (size_t)st * stage_bytes);
+                        const uint32_t w_addr = a_addr + a_bytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024, 2), make_smem_desc(w_addr + k * 32, 16, 1024, 2),
+                                      idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty[st]);
+                        if (++st == kGemmStages) { st = 0; ph ^= 1; }
+                    }
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // epilogue: thread = one row of A (TMEM lane); warps of a quadrant alternate 32-column chunks
+        const int quad = warp & 3, cgrp = (warp - 2) >> 2;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1, aph = (it >> 1) & 1;
+            const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
+            const int m = mb * 128 + quad * 32 + lane;
+            const int n0 = nb * a.n_tile;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
+            const float* bg = (EPI == GEPI_GATES && m < a.M) ? a.bias_group + (size_t)(m / a.group_rows) * a.N : nullptr;
+            for (int c0 = cgrp * 32; c0 < a.n_tile; c0 += 32 * (kGemmEpiWarps / 4)) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_base + c0, r);
+                tmem_ld_wait();
+                if (m < a.M) {
+                    const int nbase = n0 + c0;
+                    if (EPI == GEPI_GATES) {
+                        float* dst = a.out32 + (size_t)m * a.ld_out + nbase;
+                        if (nbase + 32 <= a.N && c0 + 32 <= a.n_tile) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 b4 = *reinterpret_cast<const float4*>(bg + nbase + j);
+                                float4 o = make_float4(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
+                                                       __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w);
+                                *reinterpret_cast<float4*>(dst + j) = o;
+                            }
+                        } else {
+                            for (int j = 0; j < 32 && nbase + j < a.N && c0 + j < a.n_tile; ++j) dst[j] = __uint_as_float(r[j]) + bg[nbase + j];
+                        }
+                    } else if (EPI == GEPI_FC1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nbase + j;
+                            if (n < a.N && c0 + j < a.n_tile) {
+                                float v = fmaxf(__uint_as_float(r[j]) + a.bias[n], 0.f);
+                                elt16 vh, vl;
+                                split16<ELT>(v, vh, vl);
+                                a.out_hi[(size_t)m * a.ld16 + n] = vh;
+                                if (a.out_lo) a.out_lo[(size_t)m * a.ld16 + n] = vl;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nbase + j;
+                            if (n < a.N && c0 + j < a.n_tile) {
+                                float v = sigmoid_f(__uint_as_float(r[j]) + a.bias[n]);
+                                const size_t o = (size_t)m * a.ld_out + n;
+                                a.out32[o] = v;
+                                if (a.masked) a.masked[o] = a.xmul[o] * v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// fp32 [rows][cols] (row stride ld) -> 16-bit hi/lo planes [rows][cols], optionally scaled by a power of two
+__global__ void k_split_matrix(const float* __restrict__ src, int ld, int rows, int cols, int ldo, const unsigned int* maxbits,
+                               elt16* __restrict__ bhi, elt16* __restrict__ blo, elt16* __restrict__ hhi, elt16* __restrict__ hlo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * ldo) return;
+    int c = (int)(i % ldo);
+    long long r = i / ldo;
+    if (c >= cols) { bhi[i] = blo[i] = hhi[i] = hlo[i] = 0; return; }
+    float s = 1.f;
+    if (maxbits) {
+        float m = __uint_as_float(*maxbits);
+        if (m > 0.f && isfinite(m)) { int ex; frexpf(m, &ex); s = exp2f((float)(9 - ex)); }
+    }
+    float v = s * src[r * ld + c];
+    split16<0>(v, bhi[i], blo[i]);
+    split16<1>(v, hhi[i], hlo[i]);
+}
+__global__ void k_absmax2(const float* __restrict__ w, long long n, unsigned int* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicMax(out, __float_as_uint(fabsf(w[i])));
+}
+// fp32 [rows][cols] -> hi/lo planes of one element type (activations: conv_out in the debug hook)
+__global__ void k_split_rows(const float* __restrict__ src, long long n, int elt, elt16* __restrict__ hi, elt16* __restrict__ lo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    elt16 h, l;
+    split16_rt(src[i], elt, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+struct GemmState {
+    // [elt] hi / lo planes of the three weight matrices (unscaled: fp16 lo of small LSTM/FC weights stays
+    // accurate enough in absolute terms, and the GATES epilogue needs unscaled sums)
+    elt16 *wih_hi[2] = {}, *wih_lo[2] = {};  // [8H][8F]
+    elt16 *fc1_hi[2] = {}, *fc1_lo[2] = {};  // [N1][2H]
+    elt16 *fc2_hi[2] = {}, *fc2_lo[2] = {};  // [F][N1]
+    int max_smem = 0;
+};
+static GemmState* g_state(vs_engine* e);
+
+struct TcStateHdr { void* gemm; };  // TcState (tc_conv.cu) starts with this member
+
+int tc_gemm_pack(vs_engine* e, cudaStream_t st) {
+    GemmState* g = g_state(e);
+    const int F = e->d.num_freq, H = e->d.lstm_dim, N1 = e->d.fc1_dim;
+    struct Item { const float* src; int rows, cols; elt16** hi; elt16** lo; };
+    Item items[3] = {{e->wih_x, 8 * H, 8 * F, g->wih_hi, g->wih_lo}, {e->fc1_w, N1, 2 * H, g->fc1_hi, g->fc1_lo},
+                     {e->fc2_w, F, N1, g->fc2_hi, g->fc2_lo}};
+    for (Item& it : items) {
+        const int ldo = (it.cols + 7) / 8 * 8;  // TMA needs 16-byte row strides
+        const size_t n = (size_t)it.rows * ldo;
+        for (int t = 0; t < 2; ++t) {
+            if (!it.hi[t]) {
+                VS_CUDA_TRY(cudaMalloc(&it.hi[t], n * sizeof(elt16)));
+                VS_CUDA_TRY(cudaMalloc(&it.lo[t], n * sizeof(elt16)));
+            }
+        }
+        k_split_matrix<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(it.src, it.cols, it.rows, it.cols, ldo, nullptr, it.hi[0], it.lo[0],
+                                                                    it.hi[1], it.lo[1]);
+    }
+    VS_CUDA_TRY(cudaGetLastError());
+    return VS_OK;
+}
+
+void tc_gemm_destroy(vs_engine* e) {
+    GemmState* g = g_state(e);
+    if (!g) return;
+    for (int t = 0; t < 2; ++t) {
+        cudaFree(g->wih_hi[t]); cudaFree(g->wih_lo[t]); cudaFree(g->fc1_hi[t]); cudaFree(g->fc1_lo[t]);
+        cudaFree(g->fc2_hi[t]); cudaFree(g->fc2_lo[t]);
+    }
+    delete g;
+}
+
+struct GemmWorkspace {
+    elt16 *x_hi, *x_lo;    // [M][8F]   LSTM input (cnn8 output)
+    elt16 *h_hi, *h_lo;    // [M][2H]   relu(lstm_out)
+    elt16 *y_hi, *y_lo;    // [M][N1]   relu(fc1)
+    size_t total;
+};
+static GemmWorkspace gemm_carve(const vs_engine* e, int B, int T, int precision, void* base) {
+    const int F = e->d.num_freq, H = e->d.lstm_dim, N1 = e->d.fc1_dim;
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 1024); return r; };
+    const size_t M = (size_t)B * T;
+    const bool x3 = tc_passes(precision) == 3;
+    GemmWorkspace w{};
+    w.x_hi = (elt16*)take(M * 8 * F * sizeof(elt16));
+    w.x_lo = x3 ? (elt16*)take(M * 8 * F * sizeof(elt16)) : nullptr;
+    w.h_hi = (elt16*)take(M * 2 * H * sizeof(elt16));
+    w.h_lo = x3 ? (elt16*)take(M * 2 * H * sizeof(elt16)) : nullptr;
+    const size_t N1p = (size_t)(N1 + 7) / 8 * 8;
+    w.y_hi = (elt16*)take(M * N1p * sizeof(elt16));
+    w.y_lo = x3 ? (elt16*)take(M * N1p * sizeof(elt16)) : nullptr;
+    w.total = off;
+    return w;
+}
+size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision) { return gemm_carve(e, B, T, precision, nullptr).total; }
+
+static int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt16* a_lo, const elt16* w_hi, const elt16* w_lo,
+                          GemmTcArgs a, int precision, cudaStream_t st) {
+    GemmState* g = g_state(e);
+    a.passes = tc_passes(precision);
+    const int elt = tc_elt(precision);
+    a.n_tiles_n = (a.N + 255) / 256;
+    a.n_tile = (((a.N + a.n_tiles_n - 1) / a.n_tiles_n) + 15) / 16 * 16;
+    a.n_tiles_m = (a.M + 127) / 128;
+    a.total_tiles = a.n_tiles_m * a.n_tiles_n;
+    a.n_kb = (a.K + 63) / 64;
+    if (a.lda % 8 || a.ldw % 8) { set_error("tensor-core GEMM needs 16-byte aligned operand rows (lstm_dim % 4 == 0)"); return VS_ERR_INVALID; }
+    CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
+    {
+        uint64_t ad[2] = {(uint64_t)a.K, (uint64_t)a.M}, as[1] = {(uint64_t)a.lda * sizeof(elt16)};
+        uint32_t ab[2] = {64, 128};
+        uint64_t wd[2] = {(uint64_t)a.K, (uint64_t)a.N}, ws[1] = {(uint64_t)a.ldw * sizeof(elt16)};
+        uint32_t wb[2] = {64, (uint32_t)a.n_tile};
+        bool ok = make_tmap_bf16(&tm_a_hi, (void*)a_hi, 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_a_lo, (void*)(a_lo ? a_lo : a_hi), 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_hi, (void*)w_hi, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_lo, (void*)w_lo, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!ok) { set_error("cuTensorMapEncodeTiled failed (gemm)"); return VS_ERR_CUDA; }
+    }
+    const int w_bytes_al = (a.n_tile * 128 + 1023) & ~1023;
+    const int smem = 1024 + kGemmStages * (128 * 128 + w_bytes_al) + 256;
+    if (smem > g->max_smem) { set_error("gemm tile does not fit shared memory"); return VS_ERR_UNSUPPORTED; }
+    const int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
+    cudaError_t ce = cudaSuccess;
+#define VS_GEMM_TC(E, L)                                                                                   \
+    do {                                                                                                   \
+        ce = cudaFuncSetAttribute(k_gemm_tc<E, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
+        if (ce == cudaSuccess) k_gemm_tc<E, L><<<grid, kGemmThreads, smem, st>>>(a, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo); \
+    } while (0)
+    if (epi == GEPI_GATES) { if (elt) VS_GEMM_TC(GEPI_GATES, 1); else VS_GEMM_TC(GEPI_GATES, 0); }
+    else if (epi == GEPI_FC1) { if (elt) VS_GEMM_TC(GEPI_FC1, 1); else VS_GEMM_TC(GEPI_FC1, 0); }
+    else { if (elt) VS_GEMM_TC(GEPI_FC2, 1); else VS_GEMM_TC(GEPI_FC2, 0); }
+#undef VS_GEMM_TC
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) { set_error(std::string("k_gemm_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
+    e->launches++;
+    if (e->profiling) prof_after(e, kid, st);
+    return VS_OK;
+}
+
+int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32, const float* emb,
+                 const float* x, float* mask, float* masked, int B, int T, int precision, float* xcat32, float* fc1, void* gemm_ws,
+                 const TcLstmBuffers& lb, cudaStream_t st) {
+    (void)xcat32; (void)fc1;
+    GemmState* g = g_state(e);
+    const int F = e->d.num_freq, H = e->d.lstm_dim, E = e->d.emb_dim, N1 = e->d.fc1_dim;
+    const int M = B * T, elt = tc_elt(precision);
+    const bool x3 = tc_passes(precision) == 3;
+    GemmWorkspace w = gemm_carve(e, B, T, precision, gemm_ws);
+    if (conv_out32) {
+        const long long n = (long long)M * 8 * F;
+        k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(conv_out32, n, elt, w.x_hi, w.x_lo);
+        VS_LAUNCH(e, KID_CONVERT, st, cudaGetLastError());
+    } else {
+        VS_LAUNCH(e, KID_POINT8, st, tc_launch_point8(e, plane_hi, plane_lo, elt, nullptr, w.x_hi, w.x_lo, 8 * F, B, T, st));
+    }
+    // d-vector folded into a per-utterance gate bias (tiny: B x 8H x E, fp32 FFMA)
     VS_LAUNCH(e, KID_EMB_BIAS, st, launch_gemm_fp32(emb, E, e->wih_e, E, e->b_lstm, nullptr, 1, lb.bias_u, 8 * H, B, 8 * H, E,
                                                     false, EPI_NONE, nullptr, nullptr, st));
-    VS_LAUNCH(e, KID_INPROJ, st, launch_gemm_fp32(xin, 8 * F, e->wih_x, 8 * F, nullptr, lb.bias_u, T, lb.gates, 8 * H, M, 8 * H, 8 * F,
-                                                  false, EPI_NONE, nullptr, nullptr, st));
-    VS_LAUNCH(e, KID_LSTM_REC, st, launch_lstm_rec_fp32(e, lb.gates, lb.hout, lb.hx, lb.barrier, B, T, st));
-    VS_LAUNCH(e, KID_FC1, st, launch_gemm_fp32(lb.hout, 2 * H, e->fc1_w, 2 * H, e->fc1_b, nullptr, 1, fc1, N1, M, N1, 2 * H,
-                                               true, EPI_RELU, nullptr, nullptr, st));
-    VS_LAUNCH(e, KID_FC2, st, launch_gemm_fp32(fc1, N1, e->fc2_w, N1, e->fc2_b, nullptr, 1, mask, F, M, F, N1,
-                                               false, EPI_SIGMOID_MASK, x, masked, st));
+    {   // gates_x = X * W_ih[:, :8F]^T + bias_u[utterance]
+        GemmTcArgs a{};
+        a.M = M; a.N = 8 * H; a.K = 8 * F; a.lda = 8 * F; a.ldw = 8 * F; a.group_rows = T; a.bias_group = lb.bias_u; a.out32 = lb.gates; a.ld_out = 8 * H;
+        int rc = launch_gemm_tc(e, GEPI_GATES, KID_INPROJ, w.x_hi, w.x_lo, g->wih_hi[elt], g->wih_lo[elt], a, precision, st);
+        if (rc != VS_OK) return rc;
+    }
+    VS_LAUNCH(e, KID_LSTM_REC, st, launch_lstm_rec_fp32(e, lb.gates, lb.hout, lb.hx, lb.barrier, B, T, st, w.h_hi, x3 ? w.h_lo : nullptr, elt));
+    {   // y1 = relu(relu(h) * fc1^T + b1)
+        GemmTcArgs a{};
+        a.M = M; a.N = N1; a.K = 2 * H; a.lda = 2 * H; a.ldw = (2 * H + 7) / 8 * 8; a.bias = e->fc1_b;
+        a.out_hi = w.y_hi; a.out_lo = x3 ? w.y_lo : nullptr; a.ld16 = (N1 + 7) / 8 * 8;
+        int rc = launch_gemm_tc(e, GEPI_FC1, KID_FC1, w.h_hi, w.h_lo, g->fc1_hi[elt], g->fc1_lo[elt], a, precision, st);
+        if (rc != VS_OK) return rc;
+    }
+    {   // mask = sigmoid(y1 * fc2^T + b2), masked = x * mask
+        GemmTcArgs a{};
+        a.M = M; a.N = F; a.K = N1; a.lda = (N1 + 7) / 8 * 8; a.ldw = (N1 + 7) / 8 * 8; a.bias = e->fc2_b; a.out32 = mask; a.ld_out = F; a.xmul = x; a.masked = masked;
+        int rc = launch_gemm_tc(e, GEPI_FC2, KID_FC2, w.y_hi, w.y_lo, g->fc2_hi[elt], g->fc2_lo[elt], a, precision, st);
+        if (rc != VS_OK) return rc;
+    }
     return VS_OK;
 }
 
 int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, const float* x, float* mask, int B, int T,
                        int precision, const TcLstmBuffers& lb, cudaStream_t st) {
-    float* fc1 = nullptr;
-    VS_CUDA_TRY(cudaMalloc(&fc1, (size_t)B * T * e->d.fc1_dim * sizeof(float)));
-    int rc = tc_lstm_head(e, nullptr, nullptr, conv_out, emb, x, mask, nullptr, B, T, precision, nullptr, fc1, nullptr, lb, st);
+    void* ws = nullptr;
+    VS_CUDA_TRY(cudaMalloc(&ws, tc_gemm_workspace_bytes(e, B, T, precision)));
+    int rc = tc_lstm_head(e, nullptr, nullptr, conv_out, emb, x, mask, nullptr, B, T, precision, nullptr, nullptr, ws, lb, st);
     cudaStreamSynchronize(st);
-    cudaFree(fc1);
+    cudaFree(ws);
     return rc;
+}
+
+// GemmState lives behind vs_engine::tc (TcState in tc_conv.cu keeps the pointer as its first member)
+static GemmState* g_state(vs_engine* e) {
+    TcStateHdr* hdr = (TcStateHdr*)e->tc;
+    if (!hdr->gemm) {
+        GemmState* g = new GemmState();
+        cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+        hdr->gemm = g;
+    }
+    return (GemmState*)hdr->gemm;
 }
 
 }  // namespace vs
