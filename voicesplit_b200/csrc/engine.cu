@@ -114,7 +114,10 @@ static Workspace carve(const vs_engine* e, int B, int T, int precision, void* ba
     w.gates = (float*)take(rows * 8 * H * sizeof(float));
     w.bias_u = (float*)take((size_t)B * 8 * H * sizeof(float));
     w.hout = (float*)take(rows * 2 * H * sizeof(float));
-    w.hx = (float*)take(lstm_rec_scratch_bytes(e, B));
+    {
+        size_t a = lstm_rec_scratch_bytes(e, B), b = tc_lstm_scratch_bytes(e, B);
+        w.hx = (float*)take(a > b ? a : b);
+    }
     w.barrier = (unsigned int*)take(256);
     w.total = off;
     return w;

@@ -38,6 +38,14 @@ size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision);
 int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32,
                  const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, float* xcat32,
                  float* fc1, void* gemm_ws, const TcLstmBuffers& lb, cudaStream_t st);
+// ---- tc_lstm.cu: tensor-core recurrent kernel ---------------------------------------------------
+int tc_lstm_pack(vs_engine* e, void** slot, cudaStream_t st);
+void tc_lstm_destroy(void* slot);
+size_t tc_lstm_scratch_bytes(const vs_engine* e, int B);
+int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* hout, void* scratch, elt16* hr_hi, elt16* hr_lo,
+                       int B, int T, int precision, cudaStream_t st);
+void* tc_lstm_slot(vs_engine* e);  // LstmState pointer kept in TcState (tc_conv.cu)
+
 cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
                              elt16* xlo, int ldx, int B, int T, cudaStream_t st);
 

@@ -367,6 +367,7 @@ __global__ void k_scale_tc(const float* __restrict__ scale, const unsigned int* 
 // ---------------------------------------------------------------------------------------------
 struct TcState {
     void* gemm = nullptr;     // GemmState of tc_gemm.cu (must stay the first member)
+    void* lstm = nullptr;     // LstmState of tc_lstm.cu
     elt16* w_hi[2][8] = {};   // [elt][layer]
     elt16* w_lo[2][8] = {};
     float* scale_tc[8] = {};  // BN scale divided by the layer's power-of-two weight scale
@@ -386,6 +387,7 @@ void tc_destroy(vs_engine* e) {
     TcState* s = (TcState*)e->tc;
     if (!s) return;
     tc_gemm_destroy(e);
+    tc_lstm_destroy(s->lstm);
     for (int l = 0; l < 8; ++l) {
         for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); }
         cudaFree(s->scale_tc[l]);
@@ -417,8 +419,11 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
         k_scale_tc<<<1, 64, 0, st>>>(e->conv_scale[l], s->wmax + l, s->scale_tc[l], 64);
     }
     VS_CUDA_TRY(cudaGetLastError());
+    int rc = tc_lstm_pack(e, &s->lstm, st);
+    if (rc != VS_OK) return rc;
     return tc_gemm_pack(e, st);
 }
+void* tc_lstm_slot(vs_engine* e) { return ((TcState*)e->tc)->lstm; }
 
 static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo,
                           elt16* out_hi, elt16* out_lo, int B, int T, int precision, cudaStream_t st) {

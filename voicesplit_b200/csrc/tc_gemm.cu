@@ -357,7 +357,10 @@ int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, con
         int rc = launch_gemm_tc(e, GEPI_GATES, KID_INPROJ, w.x_hi, w.x_lo, g->wih_hi[elt], g->wih_lo[elt], a, precision, st);
         if (rc != VS_OK) return rc;
     }
-    VS_LAUNCH(e, KID_LSTM_REC, st, launch_lstm_rec_fp32(e, lb.gates, lb.hout, lb.hx, lb.barrier, B, T, st, w.h_hi, x3 ? w.h_lo : nullptr, elt));
+    {
+        int rc = tc_lstm_recurrence(e, tc_lstm_slot(e), lb.gates, lb.hout, lb.hx, w.h_hi, x3 ? w.h_lo : nullptr, B, T, precision, st);
+        if (rc != VS_OK) return rc;
+    }
     {   // y1 = relu(relu(h) * fc1^T + b1)
         GemmTcArgs a{};
         a.M = M; a.N = N1; a.K = 2 * H; a.lda = 2 * H; a.ldw = (2 * H + 7) / 8 * 8; a.bias = e->fc1_b;

@@ -1,0 +1,358 @@
+// BiLSTM recurrence on tensor cores (reference nn.LSTM, models/voicesplit/model.py:57-61,82).
+//
+// Persistent kernel, one CTA per (direction, slice of 16 hidden units, group of 128 utterances).
+// The CTA keeps its 64 rows of W_hh (4 gates x 16 units, K = H) resident in shared memory as 16-bit
+// hi/lo planes for the whole sequence.  Every step it
+//   1. TMA-loads h_{t-1} of its 128 utterances ([128][H] hi/lo, written by the CTAs of the other
+//      slices) in 64-wide K blocks,
+//   2. issues  D[128 utt][64 gate cols] = h * W_slice^T  on tcgen05 (1 or 3 passes, fp32 in TMEM),
+//   3. adds the precomputed input projection gates_x, applies sigmoid/tanh, updates the cell state
+//      (registers: one thread = one utterance x 16 units, all four gates, for the whole sequence),
+//   4. writes h_t (16-bit hi/lo exchange buffer for the next step, fp32 lstm_out, and relu(h) hi/lo
+//      for the FC head) and arrives on the per-(direction, group) barrier.
+// The CTAs of one (direction, group) meet at that barrier once per step; nothing else is shared.
+#include "tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vs {
+using namespace ptx;
+
+constexpr int kLU = 16;         // hidden units per CTA
+constexpr int kLB = 128;        // utterances per CTA (MMA M)
+constexpr int kLStages = 3;     // h K-blocks in flight
+
+struct LstmTcArgs {
+    int B, T, H, nslices, ngroups, group0, nkb, nk16, passes;
+    int Bp;                       // utterance rows of the exchange buffer (multiple of 128)
+    int Hp;                       // row stride of the exchange buffer (elements, multiple of 8)
+    const float* gates_x;         // [B*T][8H]
+    float* hout;                  // [B][T][2H]
+    elt16* hx_hi;                 // [2 dir][2 parity][Bp][Hp]
+    elt16* hx_lo;
+    elt16* hr_hi;                 // [B*T][2H] relu(h), optional
+    elt16* hr_lo;
+    unsigned int* barrier;        // [2][ngroups_total]
+    int ngroups_total;
+};
+
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    // 1 / (1 + 2^(-x log2 e)): ex2.approx + rcp.approx, relative error ~2^-22
+    return __frcp_rn(1.f + exp2f(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
+
+template <int ELT>
+__global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __grid_constant__ CUtensorMap tm_w_hi,
+                                                    const __grid_constant__ CUtensorMap tm_w_lo,
+                                                    const __grid_constant__ CUtensorMap tm_h_hi,
+                                                    const __grid_constant__ CUtensorMap tm_h_lo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nplanes = a.passes == 3 ? 2 : 1;
+    uint8_t* w_smem = smem;                                            // [plane][kb][64 rows][128 B]
+    uint8_t* a_ring = smem + (size_t)nplanes * a.nkb * 8192;           // [stage][plane][128 rows][128 B]
+    const int stage_bytes = nplanes * 16384;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)kLStages * stage_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + kLStages;
+    uint64_t* w_full = a_empty + kLStages;
+    uint64_t* acc_full = w_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    // CTA coordinates
+    int cta = blockIdx.x;
+    const int slice = cta % a.nslices; cta /= a.nslices;
+    const int grp_local = cta % a.ngroups; cta /= a.ngroups;
+    const int d = cta;
+    const int grp = a.group0 + grp_local;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int* counter = a.barrier + d * a.ngroups_total + grp;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kLStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        mbar_init(w_full, 1);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 64);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- producer: W slice once, then h K-blocks every step ----------------
+            mbar_arrive_expect_tx(w_full, (uint32_t)(nplanes * a.nkb * 8192));
+            for (int p = 0; p < nplanes; ++p)
+                for (int kb = 0; kb < a.nkb; ++kb)
+                    tma_load_2d(w_smem + (size_t)(p * a.nkb + kb) * 8192, p == 0 ? &tm_w_hi : &tm_w_lo, w_full, kb * 64,
+                                (d * a.nslices + slice) * 64);
+            int st = 0, ph = 0;
+            for (int s = 1; s < a.T; ++s) {
+                // wait until every slice of this (direction, group) has published h_{s-1}
+                const unsigned int target = (unsigned int)s * a.nslices;
+                unsigned int spins = 0;
+                while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+                    if (++spins > (1u << 28)) __trap();
+                }
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy flag read -> async-proxy (TMA) data reads
+                const int par = (s - 1) & 1;                       // buffer h_{s-1} was written to
+                const int row0 = ((d * 2 + par) * a.Bp) + grp * kLB;
+                for (int kb = 0; kb < a.nkb; ++kb) {
+                    mbar_wait(&a_empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&a_full[st], (uint32_t)stage_bytes);
+                    uint8_t* dst = a_ring + (size_t)st * stage_bytes;
+                    tma_load_2d(dst, &tm_h_hi, &a_full[st], kb * 64, row0);
+                    if (nplanes == 2) tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
+                    if (++st == kLStages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const uint32_t idesc = make_idesc_bf16(128, 64, ELT);
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(w_smem);
+            int st = 0, ph = 0;
+            for (int s = 1; s < a.T; ++s) {
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < a.nkb; ++kb) {
+                    mbar_wait(&a_full[st], ph);
+                    tc_fence_after();
+                    const uint32_t h_hi = smem_u32(a_ring + (size_t)st * stage_bytes), h_lo = h_hi + 16384;
+                    const uint32_t w_hi = w_addr + (uint32_t)kb * 8192, w_lo = w_addr + (uint32_t)(a.nkb + kb) * 8192;
+                    for (int k = 0; k < 4 && kb * 4 + k < a.nk16; ++k) {
+                        umma_bf16(tmem, make_smem_desc(h_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
+                        accumulate = 1;
+                        if (nplanes == 2) {
+                            umma_bf16(tmem, make_smem_desc(h_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
+                            umma_bf16(tmem, make_smem_desc(h_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
+                        }
+                    }
+                    umma_commit(&a_empty[st]);
+                    if (++st == kLStages) { st = 0; ph ^= 1; }
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        // ---------------- cell update: thread = one utterance, 16 units ----------------
+        const int quad = warp & 3;
+        const int b = grp * kLB + quad * 32 + lane;          // utterance handled by this thread
+        const bool valid = b < a.B;
+        const int u0 = slice * kLU;                          // first hidden unit of the slice
+        const int nu = min(kLU, a.H - u0);                   // valid units in this slice
+        float c[kLU];
+#pragma unroll
+        for (int j = 0; j < kLU; ++j) c[j] = 0.f;
+        const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16);
+        for (int s = 0; s < a.T; ++s) {
+            const int t = d ? a.T - 1 - s : s;
+            // input projection for this step (issued before waiting on the MMA)
+            float gx[4][kLU];
+            const float* gsrc = a.gates_x + ((size_t)(valid ? b : 0) * a.T + t) * 8 * a.H + (size_t)d * 4 * a.H + u0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (nu == kLU && (a.H & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < kLU; j += 4) {
+                        float4 v = __ldg(reinterpret_cast<const float4*>(gsrc + (size_t)g * a.H + j));
+                        gx[g][j] = v.x; gx[g][j + 1] = v.y; gx[g][j + 2] = v.z; gx[g][j + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kLU; ++j) gx[g][j] = j < nu ? __ldg(gsrc + (size_t)g * a.H + j) : 0.f;
+                }
+            }
+            if (s > 0) {
+                mbar_wait(acc_full, (s - 1) & 1);
+                tc_fence_after();
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(t_base, r0);
+                tmem_ld_32x32(t_base + 32, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < kLU; ++j) {
+                    gx[0][j] += __uint_as_float(r0[j]);
+                    gx[1][j] += __uint_as_float(r0[16 + j]);
+                    gx[2][j] += __uint_as_float(r1[j]);
+                    gx[3][j] += __uint_as_float(r1[16 + j]);
+                }
+                tc_fence_before();
+            }
+            const int par = s & 1;
+            elt16* hx_hi = a.hx_hi + ((size_t)(d * 2 + par) * a.Bp + (valid ? b : 0)) * a.Hp + u0;
+            elt16* hx_lo = a.hx_lo ? a.hx_lo + ((size_t)(d * 2 + par) * a.Bp + (valid ? b : 0)) * a.Hp + u0 : nullptr;
+            const size_t oidx = ((size_t)(valid ? b : 0) * a.T + t) * 2 * a.H + (size_t)d * a.H + u0;
+            __align__(16) elt16 vh[kLU], vl[kLU], rh[kLU], rl[kLU];
+            float hv[kLU];
+#pragma unroll
+            for (int j = 0; j < kLU; ++j) {
+                const float ig = sigmoid_fast(gx[0][j]), fg = sigmoid_fast(gx[1][j]);
+                const float gg = tanh_fast(gx[2][j]), og = sigmoid_fast(gx[3][j]);
+                c[j] = fmaf(fg, c[j], ig * gg);
+                hv[j] = og * tanh_fast(c[j]);
+                split16<ELT>(hv[j], vh[j], vl[j]);
+                split16<ELT>(fmaxf(hv[j], 0.f), rh[j], rl[j]);
+            }
+            if (valid) {
+                if (nu == kLU && (a.H & 7) == 0) {
+                    *reinterpret_cast<uint4*>(hx_hi) = *reinterpret_cast<const uint4*>(vh);
+                    *reinterpret_cast<uint4*>(hx_hi + 8) = *reinterpret_cast<const uint4*>(vh + 8);
+                    if (hx_lo) {
+                        *reinterpret_cast<uint4*>(hx_lo) = *reinterpret_cast<const uint4*>(vl);
+                        *reinterpret_cast<uint4*>(hx_lo + 8) = *reinterpret_cast<const uint4*>(vl + 8);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kLU; j += 4)
+                        *reinterpret_cast<float4*>(a.hout + oidx + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
+                    if (a.hr_hi) {
+                        *reinterpret_cast<uint4*>(a.hr_hi + oidx) = *reinterpret_cast<const uint4*>(rh);
+                        *reinterpret_cast<uint4*>(a.hr_hi + oidx + 8) = *reinterpret_cast<const uint4*>(rh + 8);
+                        if (a.hr_lo) {
+                            *reinterpret_cast<uint4*>(a.hr_lo + oidx) = *reinterpret_cast<const uint4*>(rl);
+                            *reinterpret_cast<uint4*>(a.hr_lo + oidx + 8) = *reinterpret_cast<const uint4*>(rl + 8);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kLU; ++j) {
+                        if (j < nu) {
+                            hx_hi[j] = vh[j];
+                            if (hx_lo) hx_lo[j] = vl[j];
+                            a.hout[oidx + j] = hv[j];
+                            if (a.hr_hi) { a.hr_hi[oidx + j] = rh[j]; if (a.hr_lo) a.hr_lo[oidx + j] = rl[j]; }
+                        }
+                    }
+                }
+            }
+            if (s + 1 < a.T) {
+                // publish h_s: all 128 cell threads have stored, then one of them releases the counter
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    __threadfence();
+                    atomicAdd(counter, 1u);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 64);
+}
+
+// W_hh [2][4H][H] fp32 -> [2][nslices*64][Hp] 16-bit hi/lo, row = slice*64 + gate*16 + j
+__global__ void k_pack_whh_tc(const float* __restrict__ whh, int H, int Hp, int nslices, elt16* __restrict__ bhi, elt16* __restrict__ blo,
+                              elt16* __restrict__ hhi, elt16* __restrict__ hlo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)2 * nslices * 64 * Hp;
+    if (i >= n) return;
+    int k = (int)(i % Hp);
+    long long r = i / Hp;
+    int row = (int)(r % 64), sl = (int)((r / 64) % nslices), d = (int)(r / (64LL * nslices));
+    int g = row / kLU, j = row % kLU, u = sl * kLU + j;
+    float v = (u < H && k < H) ? whh[((size_t)d * 4 * H + (size_t)g * H + u) * H + k] : 0.f;
+    split16<0>(v, bhi[i], blo[i]);
+    split16<1>(v, hhi[i], hlo[i]);
+}
+
+struct LstmState {
+    elt16 *w_hi[2] = {}, *w_lo[2] = {};
+    int max_smem = 0;
+};
+
+int tc_lstm_pack(vs_engine* e, void** slot, cudaStream_t st) {
+    if (!*slot) {
+        LstmState* s = new LstmState();
+        cudaDeviceGetAttribute(&s->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+        *slot = s;
+    }
+    LstmState* s = (LstmState*)*slot;
+    const int H = e->d.lstm_dim, Hp = (H + 7) / 8 * 8, nslices = (H + kLU - 1) / kLU;
+    const size_t n = (size_t)2 * nslices * 64 * Hp;
+    for (int t = 0; t < 2; ++t) {
+        if (!s->w_hi[t]) {
+            VS_CUDA_TRY(cudaMalloc(&s->w_hi[t], n * sizeof(elt16)));
+            VS_CUDA_TRY(cudaMalloc(&s->w_lo[t], n * sizeof(elt16)));
+        }
+    }
+    k_pack_whh_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->whh, H, Hp, nslices, s->w_hi[0], s->w_lo[0], s->w_hi[1], s->w_lo[1]);
+    VS_CUDA_TRY(cudaGetLastError());
+    return VS_OK;
+}
+void tc_lstm_destroy(void* slot) {
+    LstmState* s = (LstmState*)slot;
+    if (!s) return;
+    for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t]); cudaFree(s->w_lo[t]); }
+    delete s;
+}
+
+size_t tc_lstm_scratch_bytes(const vs_engine* e, int B) {
+    const int H = e->d.lstm_dim, Hp = (H + 7) / 8 * 8;
+    const size_t Bp = align_up((size_t)B, kLB);
+    // hi + lo exchange buffers [2][2][Bp][Hp] + barrier counters
+    return 2 * (size_t)4 * Bp * Hp * sizeof(elt16) + 4096;
+}
+
+int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* hout, void* scratch, elt16* hr_hi, elt16* hr_lo,
+                       int B, int T, int precision, cudaStream_t st) {
+    LstmState* s = (LstmState*)slot;
+    const int H = e->d.lstm_dim, Hp = (H + 7) / 8 * 8, nslices = (H + kLU - 1) / kLU;
+    const int elt = tc_elt(precision), passes = tc_passes(precision);
+    const int Bp = (int)align_up((size_t)B, kLB);
+    const int ngroups_total = Bp / kLB;
+    LstmTcArgs a{};
+    a.B = B; a.T = T; a.H = H; a.nslices = nslices; a.nkb = (H + 63) / 64; a.nk16 = (H + 15) / 16; a.passes = passes;
+    a.Bp = Bp; a.Hp = Hp; a.gates_x = gates_x; a.hout = hout;
+    char* p = (char*)scratch;
+    const size_t plane = (size_t)4 * Bp * Hp * sizeof(elt16);
+    a.hx_hi = (elt16*)p;
+    a.hx_lo = passes == 3 ? (elt16*)(p + plane) : nullptr;
+    a.barrier = (unsigned int*)(p + 2 * plane);
+    a.hr_hi = hr_hi; a.hr_lo = passes == 3 ? hr_lo : nullptr;
+    a.ngroups_total = ngroups_total;
+    if (2 * ngroups_total * (int)sizeof(unsigned int) > 4096) { set_error("batch too large for the LSTM barrier table"); return VS_ERR_INVALID; }
+    const int nplanes = passes == 3 ? 2 : 1;
+    const int smem = 1024 + nplanes * a.nkb * 8192 + kLStages * nplanes * 16384 + 256;
+    if (smem > s->max_smem) { set_error("lstm_dim too large for the tensor-core recurrent kernel"); return VS_ERR_UNSUPPORTED; }
+    const int max_groups = e->num_sms / (2 * nslices);
+    if (max_groups < 1) { set_error("lstm_dim too large: one step of all slices must be co-resident"); return VS_ERR_UNSUPPORTED; }
+    CUtensorMap tm_w_hi, tm_w_lo, tm_h_hi, tm_h_lo;
+    {
+        uint64_t wd[2] = {(uint64_t)H, (uint64_t)2 * nslices * 64}, ws[1] = {(uint64_t)Hp * sizeof(elt16)};
+        uint32_t wb[2] = {64, 64};
+        uint64_t hd[2] = {(uint64_t)H, (uint64_t)4 * Bp}, hs[1] = {(uint64_t)Hp * sizeof(elt16)};
+        uint32_t hb[2] = {64, 128};
+        bool ok = make_tmap_bf16(&tm_w_hi, s->w_hi[elt], 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_lo, s->w_lo[elt], 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_h_hi, a.hx_hi, 2, hd, hs, hb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_h_lo, a.hx_lo ? a.hx_lo : a.hx_hi, 2, hd, hs, hb, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!ok) { set_error("cuTensorMapEncodeTiled failed (lstm)"); return VS_ERR_CUDA; }
+    }
+    cudaError_t ce = cudaMemsetAsync(a.barrier, 0, 4096, st);
+    if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return VS_ERR_CUDA; }
+    const void* fn = elt ? (const void*)k_lstm_tc<1> : (const void*)k_lstm_tc<0>;
+    ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return VS_ERR_CUDA; }
+    // groups of 128 utterances are independent: run as many as are co-resident per launch
+    for (int g0 = 0; g0 < ngroups_total; g0 += max_groups) {
+        a.group0 = g0;
+        a.ngroups = ngroups_total - g0 < max_groups ? ngroups_total - g0 : max_groups;
+        void* args[] = {(void*)&a, (void*)&tm_w_hi, (void*)&tm_w_lo, (void*)&tm_h_hi, (void*)&tm_h_lo};
+        ce = cudaLaunchCooperativeKernel(fn, dim3(2 * a.ngroups * nslices), dim3(192), args, (size_t)smem, st);
+        if (ce != cudaSuccess) { set_error(std::string("k_lstm_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
+        e->launches++;
+    }
+    if (e->profiling) prof_after(e, KID_LSTM_REC, st);
+    return VS_OK;
+}
+
+}  // namespace vs
