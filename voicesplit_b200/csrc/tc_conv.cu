@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int useful = a.N - 1;
-    // per (dt): which (weight plane, strip plane) passes run.  bf16x3 = hi*hi + lo*hi + hi*lo,
-    // ordered so the hi strip is loaded once for the first two.
+    // 3-pass modes: per tap row both strips (hi, lo) are resident; each weight tile is fetched once:
+    // W_hi[j] multiplies S_hi and S_lo, W_lo[j] multiplies S_hi  (hi*hi + lo*hi + hi*lo).
     const int n_strip_loads = a.passes == 3 ? 2 : 1;
 
     if (warp == 0) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                 const int q0 = (tile - b * a.tiles_per_utt) * useful;
                 for (int dt = 0; dt < a.n_dt; ++dt) {
                     const int qs = q0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
-                    for (int sp = 0; sp < n_strip_loads; ++sp) {  // strip plane: 0 = hi, 1 = lo
+                    for (int sp = 0; sp < n_strip_loads; ++sp) {  // strip planes of this tap row: hi (, lo)
                         mbar_wait(&s_empty[ss], sph ^ 1);
                         mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
                         uint8_t* dst = s_ring + (size_t)ss * strip_bytes;
@@ -117,16 +117,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                             tma_load_3d(dst + (size_t)i * a.box_rows * 128, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[ss], 0,
                                         qs + i * a.box_rows, b);
                         if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
-                        // weight planes used against this strip: hi strip -> W hi (, W lo); lo strip -> W hi
-                        const int n_wp = (a.passes == 3 && sp == 0) ? 2 : 1;
-                        for (int wp = 0; wp < n_wp; ++wp) {
-                            for (int j = 0; j < a.n_j; ++j) {
-                                mbar_wait(&w_empty[ws], wph ^ 1);
-                                mbar_arrive_expect_tx(&w_full[ws], kWTileBytes);
-                                tma_load_2d(w_ring + (size_t)ws * kWTileBytes, wp == 0 ? &tm_w_hi : &tm_w_lo, &w_full[ws], 0,
-                                            (dt * a.n_j + j) * 128);
-                                if (++ws == kWStages) { ws = 0; wph ^= 1; }
-                            }
+                    }
+                    // weight tiles of this tap row: W_hi[j] (used against both strips), then W_lo[j]
+                    for (int j = 0; j < a.n_j; ++j) {
+                        for (int wp = 0; wp < n_strip_loads; ++wp) {
+                            mbar_wait(&w_empty[ws], wph ^ 1);
+                            mbar_arrive_expect_tx(&w_full[ws], kWTileBytes);
+                            tma_load_2d(w_ring + (size_t)ws * kWTileBytes, wp == 0 ? &tm_w_hi : &tm_w_lo, &w_full[ws], 0,
+                                        (dt * a.n_j + j) * 128);
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                     }
                 }
@@ -144,30 +143,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                 const uint32_t d_tmem = tmem + (uint32_t)(buf * a.N);
                 uint32_t accumulate = 0;
                 for (int dt = 0; dt < a.n_dt; ++dt) {
+                    // strips of this tap row: hi in stage ss (, lo in the next stage)
+                    uint32_t s_addr[2];
+                    int s_stage[2];
                     for (int sp = 0; sp < n_strip_loads; ++sp) {
                         mbar_wait(&s_full[ss], sph);
-                        tc_fence_after();
-                        const uint32_t s_addr = smem_u32(s_ring + (size_t)ss * strip_bytes);
-                        const int n_wp = (a.passes == 3 && sp == 0) ? 2 : 1;
-                        for (int wp = 0; wp < n_wp; ++wp) {
-                            for (int j = 0; j < a.n_j; ++j) {
-                                mbar_wait(&w_full[ws], wph);
-                                tc_fence_after();
-                                const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWTileBytes);
-                                const uint32_t b_addr = s_addr + (uint32_t)(2 * j) * 128;
+                        s_addr[sp] = smem_u32(s_ring + (size_t)ss * strip_bytes);
+                        s_stage[sp] = ss;
+                        if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
+                    }
+                    tc_fence_after();
+                    for (int j = 0; j < a.n_j; ++j) {
+                        for (int wp = 0; wp < n_strip_loads; ++wp) {   // wp 0: W_hi x (S_hi, S_lo); wp 1: W_lo x S_hi
+                            mbar_wait(&w_full[ws], wph);
+                            tc_fence_after();
+                            const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWTileBytes);
+                            const int n_sp = (wp == 0) ? n_strip_loads : 1;
+                            for (int sp = 0; sp < n_sp; ++sp) {
+                                const uint32_t b_addr = s_addr[sp] + (uint32_t)(2 * j) * 128;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
                                               idesc, accumulate);
                                     accumulate = 1;
                                 }
-                                umma_commit(&w_empty[ws]);
-                                if (++ws == kWStages) { ws = 0; wph ^= 1; }
                             }
+                            umma_commit(&w_empty[ws]);
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
-                        umma_commit(&s_empty[ss]);
-                        if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
                     }
+                    for (int sp = 0; sp < n_strip_loads; ++sp) umma_commit(&s_empty[s_stage[sp]]);
                 }
                 umma_commit(&acc_full[buf]);
             }
@@ -230,38 +235,52 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
 // ---------------------------------------------------------------------------------------------
 // cnn1 on CUDA cores, writing the bf16 hi/lo planes (K = 7, C_in = 1: not MMA-shaped)
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, int ELT>
 __global__ void __launch_bounds__(256) k_front_tc(const float* __restrict__ x, elt16* __restrict__ hi,
                                                   elt16* __restrict__ lo, const float* __restrict__ w,
                                                   const float* __restrict__ scale, const float* __restrict__ shift,
-                                                  int T, int F, int Fp, int elt) {
-    __shared__ float xs[32 + 6];
-    __shared__ float ws[7 * 64];
-    __shared__ float sc[64], sh[64];
-    const int f0 = blockIdx.x * 32, t = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
-    const float* xrow = x + ((size_t)b * T + t) * F;
-    if (tid < 38) {
-        int f = f0 + tid - 3;
-        xs[tid] = (f >= 0 && f < F) ? xrow[f] : 0.f;
-    }
-    for (int i = tid; i < 7 * 64; i += 256) ws[i] = w[i];
-    if (tid < 64) { sc[tid] = scale[tid]; sh[tid] = shift[tid]; }
-    __syncthreads();
-    const int px = tid >> 3, cg = tid & 7, f = f0 + px;
-    if (f >= Fp) return;
-    __align__(16) elt16 vh[8], vl[8];
+                                                  int F, int Fp, int nrows) {
+    // one block per (utterance, frame) row; thread = 8 output channels x 2 adjacent pixels, its 56
+    // filter taps live in registers for the whole row
+    extern __shared__ float xs[];   // [Fp + 8]: x[f - 3] at xs[f]
+    const int tid = threadIdx.x, cg = tid & 7, pp = tid >> 3;
+    float wr[7][8], sc[8], sh[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        int co = cg * 8 + c;
-        float acc = 0.f;
+        sc[c] = scale[cg * 8 + c]; sh[c] = shift[cg * 8 + c];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc = fmaf(ws[j * 64 + co], xs[px + j], acc);
-        float y = (f < F) ? activate<ACT>(fmaf(acc, sc[co], sh[co])) : 0.f;
-        split16_rt(y, elt, vh[c], vl[c]);
+        for (int j = 0; j < 7; ++j) wr[j][c] = w[j * 64 + cg * 8 + c];
     }
-    size_t o = (((size_t)b * T + t) * Fp + f) * 64 + cg * 8;
-    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(vh);
-    if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(vl);
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const float* xrow = x + (size_t)row * F;
+        __syncthreads();
+        for (int i = tid; i < Fp + 8; i += 256) {
+            int f = i - 3;
+            xs[i] = (f >= 0 && f < F) ? xrow[f] : 0.f;
+        }
+        __syncthreads();
+        for (int f0 = pp * 2; f0 < Fp; f0 += 64) {
+            float xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = xs[f0 + i];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int f = f0 + p;
+                __align__(16) elt16 vh[8], vl[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc = fmaf(wr[j][c], xv[p + j], acc);
+                    float y = (f < F) ? act_fast<ACT>(fmaf(acc, sc[c], sh[c])) : 0.f;
+                    split16<ELT>(y, vh[c], vl[c]);
+                }
+                const size_t o = ((size_t)row * Fp + f) * 64 + cg * 8;
+                *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(vh);
+                if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(vl);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,37 +292,62 @@ __global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi,
                                                    const float* __restrict__ w, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, float* __restrict__ x32,
                                                    elt16* __restrict__ xhi, elt16* __restrict__ xlo, int ldx,
-                                                   int F, int Fp, long long npix) {
-    __shared__ float ws[64 * 8];
+                                                   int F, int Fp, long long nplane) {
+    // 256 consecutive plane pixels per block.  The 2 x 32 KB of channel data are staged through shared
+    // memory with fully coalesced 16-byte copies (rows padded to 144 B: conflict-free 16-byte reads),
+    // then one thread per pixel does the 64 -> 8 contraction.
+    extern __shared__ __align__(16) uint8_t stage[];
+    __shared__ __align__(16) float ws[64 * 8];
     __shared__ float sc[8], sh[8];
-    for (int i = threadIdx.x; i < 512; i += 256) ws[i] = w[i];
-    if (threadIdx.x < 8) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 512; i += 256) ws[i] = w[i];
+    if (tid < 8) { sc[tid] = scale[tid]; sh[tid] = shift[tid]; }
+    const long long p0 = (long long)blockIdx.x * 256;
+    uint8_t* s_hi = stage;
+    uint8_t* s_lo = stage + 256 * 144;
+    const int nplanes = lo ? 2 : 1;
+    for (int pl = 0; pl < nplanes; ++pl) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(pl == 0 ? hi : lo) + p0 * 128;
+        uint8_t* dst = pl == 0 ? s_hi : s_lo;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int chunk = i * 256 + tid;
+            const int px = chunk >> 3, part = chunk & 7;
+            if (p0 + px < nplane) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + px * 144 + part * 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)chunk * 16) : "memory");
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    long long p = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (p >= npix) return;
-    int f = (int)(p % F);
-    long long bt = p / F;
-    const uint4* sh4 = reinterpret_cast<const uint4*>(hi + ((size_t)bt * Fp + f) * 64);
-    const uint4* sl4 = lo ? reinterpret_cast<const uint4*>(lo + ((size_t)bt * Fp + f) * 64) : nullptr;
+    const long long p = p0 + tid;
+    if (p >= nplane) return;
+    const int f = (int)(p % Fp);
+    if (f >= F) return;
+    const long long bt = p / Fp;
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll 2
     for (int q = 0; q < 8; ++q) {
-        uint4 vh = sh4[q];
-        uint4 vl = sl4 ? sl4[q] : make_uint4(0, 0, 0, 0);
+        const uint4 vh = *reinterpret_cast<const uint4*>(s_hi + tid * 144 + q * 16);
+        const uint4 vl = lo ? *reinterpret_cast<const uint4*>(s_lo + tid * 144 + q * 16) : make_uint4(0, 0, 0, 0);
         const elt16* ph = reinterpret_cast<const elt16*>(&vh);
         const elt16* pl = reinterpret_cast<const elt16*>(&vl);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float v = join16(ph[k], pl[k], elt);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, ws[(q * 8 + k) * 8 + c], acc[c]);
+            const float v = join16(ph[k], pl[k], elt);
+            const float4 w0 = *reinterpret_cast<const float4*>(ws + (q * 8 + k) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(ws + (q * 8 + k) * 8 + 4);
+            acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+            acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
         }
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        float y = activate<ACT>(fmaf(acc[c], sc[c], sh[c]));
+        float y = act_fast<ACT>(fmaf(acc[c], sc[c], sh[c]));
         size_t o = (size_t)bt * ldx + (size_t)c * F + f;
         if (x32) x32[o] = y;
         if (xhi) {
@@ -491,23 +535,32 @@ static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt
 
 static cudaError_t launch_front_tc(const vs_engine* e, const float* x, elt16* hi, elt16* lo, int elt, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
-    dim3 grid((Fp + 31) / 32, T, B);
-    if (e->d.activation == VS_ACT_RELU)
-        k_front_tc<VS_ACT_RELU><<<grid, 256, 0, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], T, F, Fp, elt);
-    else
-        k_front_tc<VS_ACT_MISH><<<grid, 256, 0, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], T, F, Fp, elt);
+    const int nrows = B * T;
+    const int grid = nrows < e->num_sms * 8 ? nrows : e->num_sms * 8;
+    const size_t smem = (size_t)(Fp + 8) * sizeof(float);
+#define VS_FRONT(A, E) k_front_tc<A, E><<<grid, 256, smem, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], F, Fp, nrows)
+    if (e->d.activation == VS_ACT_RELU) { if (elt) VS_FRONT(VS_ACT_RELU, 1); else VS_FRONT(VS_ACT_RELU, 0); }
+    else { if (elt) VS_FRONT(VS_ACT_MISH, 1); else VS_FRONT(VS_ACT_MISH, 0); }
+#undef VS_FRONT
     return cudaGetLastError();
 }
 
 static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32,
                                     elt16* xhi, elt16* xlo, int ldx, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
-    long long npix = (long long)B * T * F;
-    unsigned grid = (unsigned)((npix + 255) / 256);
-    if (e->d.activation == VS_ACT_RELU)
-        k_point8_tc<VS_ACT_RELU><<<grid, 256, 0, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, npix);
-    else
-        k_point8_tc<VS_ACT_MISH><<<grid, 256, 0, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, npix);
+    const long long nplane = (long long)B * T * Fp;
+    const unsigned grid = (unsigned)((nplane + 255) / 256);
+    const int smem = 2 * 256 * 144;
+    cudaError_t ce;
+    if (e->d.activation == VS_ACT_RELU) {
+        ce = cudaFuncSetAttribute(k_point8_tc<VS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (ce != cudaSuccess) return ce;
+        k_point8_tc<VS_ACT_RELU><<<grid, 256, smem, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, nplane);
+    } else {
+        ce = cudaFuncSetAttribute(k_point8_tc<VS_ACT_MISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (ce != cudaSuccess) return ce;
+        k_point8_tc<VS_ACT_MISH><<<grid, 256, smem, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, nplane);
+    }
     return cudaGetLastError();
 }
 
