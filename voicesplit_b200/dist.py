@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing of the mask path: utterances are independent in the forward pass (eval-mode
+BatchNorm uses running statistics, LSTM state is per utterance), so a batch is sharded across ranks
+with NO data-path collective.  torch.distributed is used only to launch one
+process per GPU, to barrier around the timed region and to take the max of the per-rank timings."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init(backend, device=None):
+    """Initialise the default process group when WORLD_SIZE > 1; returns torch.distributed or None."""
+    _, world, _ = env_rank()
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kw)
+    return dist
+
+
+def shard(global_batch, rank, world):
+    """[start, stop) of the utterances rank `rank` owns when `global_batch` utterances are split as
+    evenly as possible (the first `global_batch % world` ranks take one more)."""
+    base, extra = divmod(global_batch, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def max_over_ranks(value, dist, device="cpu"):
+    if dist is None:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, dist, device="cpu"):
+    if dist is None:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def aggregate_throughput(local_units, local_ms, dist, device="cpu"):
+    """Whole-job throughput = units processed by all ranks / max-over-ranks time."""
+    total = sum_over_ranks(local_units, dist, device)
+    ms = max_over_ranks(local_ms, dist, device)
+    return total / (ms / 1e3), ms
