@@ -151,3 +151,46 @@ def test_batch_independence_and_host_entry():
         mh = torch.empty_like(xh).pin_memory()
         eng.forward_host(xh, eh, mh, precision=precision)
         assert torch.equal(mh, full.cpu())
+
+
+def test_abi_error_paths():
+    """Errors surface as codes + messages, never as silent fallbacks."""
+    import ctypes
+    from voicesplit_b200 import _cabi
+    lib = _cabi.load()
+    dims = synth.make_dims(33, 16, 24, 40)
+    eng = MaskEngine(activation="mish", **dims)
+    x = torch.zeros(1, 4, 33, device="cuda"); emb = torch.zeros(1, 16, device="cuda"); out = torch.empty_like(x)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    # parameters not loaded yet
+    rc = lib.vs_forward(eng.handle, P(x), P(emb), P(out), None, 1, 4, 0, P(ws), ws.numel(), None)
+    assert rc == -3 and b"not loaded" in lib.vs_last_error()
+    sd = synth.make_state_dict(dims, 1, "default")
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    assert lib.vs_forward(eng.handle, P(x), P(emb), P(out), None, 1, 4, 99, P(ws), ws.numel(), None) == -1   # bad precision
+    assert lib.vs_forward(eng.handle, P(x), P(emb), P(out), None, 0, 4, 0, P(ws), ws.numel(), None) == -1    # B < 1
+    assert lib.vs_forward(eng.handle, P(x), P(emb), P(out), None, 1, 4, 0, P(ws), 16, None) == -3            # workspace too small
+    assert b"workspace" in lib.vs_last_error()
+    assert lib.vs_forward(eng.handle, None, P(emb), P(out), None, 1, 4, 0, P(ws), ws.numel(), None) == -1    # null input
+    bad = _cabi.VsDims(33, 16, 24, 40, 34, 0)                                                                # fc2_dim != num_freq
+    h = ctypes.c_void_p()
+    assert lib.vs_engine_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(1, 4, 32, device="cuda"), emb)
+
+
+def test_fp16_modes_stay_finite_on_huge_activations():
+    """Half has a narrow exponent: activations are clamped before conversion, so even absurd weights
+    give a finite mask (bf16x3 is the mode without the range caveat and must still match fp32)."""
+    dims = synth.make_dims(33, 16, 24, 40)
+    sd = synth.make_state_dict(dims, 9, "default")
+    sd["conv.2.weight"] = sd["conv.2.weight"] * 3e5          # BatchNorm gamma of cnn1: activations ~1e5
+    eng = MaskEngine(activation="relu", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    x, emb = synth.make_inputs(2, 19, dims, 4)
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
+    ref = eng.forward(xt, et, precision="fp32")
+    for p in ("fp16x3", "fp16"):
+        assert torch.isfinite(eng.forward(xt, et, precision=p)).all()
+    assert (eng.forward(xt, et, precision="bf16x3") - ref).abs().max() < 1e-3

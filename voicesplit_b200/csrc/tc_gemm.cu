@@ -7,14 +7,15 @@
 //   FC2   : + bias, sigmoid, * spectrogram                             -> mask (and masked) fp32
 // Tile: 128 rows of A (the MMA M, one TMEM lane per row) x n_tile <= 256 rows of W (the MMA N).
 // K is walked in 64-element blocks (one 128-byte swizzle atom per row); TMA zero-fills the K and
-// N tails, so nothing is padded in memory.  Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.
+// N tails, so nothing is padded in memory.  In the 3-pass modes one pipeline stage holds all four
+// operand tiles of a K block (A_hi, A_lo, W_hi, W_lo: each fetched once) and the issuer runs
+// hi*hi + lo*hi + hi*lo on it.  Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
 
 namespace vs {
 using namespace ptx;
 
-constexpr int kGemmStages = 4;
 constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2 };
@@ -23,7 +24,7 @@ struct GemmTcArgs {
     int M, N, K;
     int lda, ldw;               // row strides (elements) of the 16-bit A and W planes, multiples of 8
     int n_tile, n_tiles_n, n_tiles_m, total_tiles, n_kb;
-    int passes;
+    int passes, stages;
     int group_rows;             // GATES: rows per utterance (T)
     const float* bias;          // [N] (FC1/FC2) or null
     const float* bias_group;    // [M / group_rows][N] (GATES)
@@ -45,17 +46,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = 128 * 128, w_bytes = a.n_tile * 128;
     const int w_bytes_al = (w_bytes + 1023) & ~1023;
-    const int stage_bytes = a_bytes + w_bytes_al;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGemmStages * stage_bytes);
+    const int nplanes = a.passes == 3 ? 2 : 1;
+    const int stage_bytes = nplanes * (a_bytes + w_bytes_al);   // [A_hi][A_lo][W_hi][W_lo]
+    const int nst = a.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nst * stage_bytes);
     uint64_t* full = bars;
-    uint64_t* empty = bars + kGemmStages;
-    uint64_t* acc_full = empty + kGemmStages;
+    uint64_t* empty = bars + nst;
+    uint64_t* acc_full = empty + nst;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < nst; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGemmEpiWarps); }
         fence_barrier_init();
         prefetch_tensormap(&tm_a_hi); prefetch_tensormap(&tm_w_hi);
@@ -74,18 +77,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
             int st = 0, ph = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
-                for (int pass = 0; pass < a.passes; ++pass) {
-                    // pass 0: A_hi*W_hi, pass 1: A_lo*W_hi, pass 2: A_hi*W_lo
-                    const CUtensorMap* ta = pass == 1 ? &tm_a_lo : &tm_a_hi;
-                    const CUtensorMap* tw = pass == 2 ? &tm_w_lo : &tm_w_hi;
-                    for (int kb = 0; kb < a.n_kb; ++kb) {
-                        mbar_wait(&empty[st], ph ^ 1);
-                        mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + w_bytes));
-                        uint8_t* dst = smem + (size_t)st * stage_bytes;
-                        tma_load_2d(dst, ta, &full[st], kb * 64, mb * 128);
-                        tma_load_2d(dst + a_bytes, tw, &full[st], kb * 64, nb * a.n_tile);
-                        if (++st == kGemmStages) { st = 0; ph ^= 1; }
-                    }
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)(nplanes * (a_bytes + w_bytes)));
+                    uint8_t* dst = smem + (size_t)st * stage_bytes;
+                    tma_load_2d(dst, &tm_a_hi, &full[st], kb * 64, mb * 128);
+                    if (nplanes == 2) tma_load_2d(dst + a_bytes, &tm_a_lo, &full[st], kb * 64, mb * 128);
+                    tma_load_2d(dst + nplanes * a_bytes, &tm_w_hi, &full[st], kb * 64, nb * a.n_tile);
+                    if (nplanes == 2) tma_load_2d(dst + nplanes * a_bytes + w_bytes_al, &tm_w_lo, &full[st], kb * 64, nb * a.n_tile);
+                    if (++st == nst) { st = 0; ph ^= 1; }
                 }
             }
         }
@@ -99,21 +99,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)(buf * 256);
                 uint32_t accumulate = 0;
-                for (int pass = 0; pass < a.passes; ++pass) {
-                    for (int kb = 0; kb < a.n_kb; ++kb) {
-                        mbar_wait(&full[st], ph);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + (size_t)st * stage_bytes);
-                        const uint32_t w_addr = a_addr + a_bytes;
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)st * stage_bytes), a_lo = a_hi + a_bytes;
+                    const uint32_t w_hi = a_hi + nplanes * a_bytes, w_lo = w_hi + w_bytes_al;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024, 2), make_smem_desc(w_addr + k * 32, 16, 1024, 2),
-                                      idesc, accumulate);
-                            accumulate = 1;
+                    for (int k = 0; k < 4; ++k) {
+                        umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
+                        accumulate = 1;
+                        if (nplanes == 2) {
+                            umma_bf16(d_tmem, make_smem_desc(a_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
+                            umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
                         }
-                        umma_commit(&empty[st]);
-                        if (++st == kGemmStages) { st = 0; ph ^= 1; }
                     }
+                    umma_commit(&empty[st]);
+                    if (++st == nst) { st = 0; ph ^= 1; }
                 }
                 umma_commit(&acc_full[buf]);
             }
@@ -312,8 +313,11 @@ static int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, con
         if (!ok) { set_error("cuTensorMapEncodeTiled failed (gemm)"); return VS_ERR_CUDA; }
     }
     const int w_bytes_al = (a.n_tile * 128 + 1023) & ~1023;
-    const int smem = 1024 + kGemmStages * (128 * 128 + w_bytes_al) + 256;
-    if (smem > g->max_smem) { set_error("gemm tile does not fit shared memory"); return VS_ERR_UNSUPPORTED; }
+    const int stage_bytes = (a.passes == 3 ? 2 : 1) * (128 * 128 + w_bytes_al);
+    a.stages = (g->max_smem - 1024 - 512) / stage_bytes;
+    if (a.stages > 6) a.stages = 6;
+    if (a.stages < 2) { set_error("gemm tile does not fit shared memory"); return VS_ERR_UNSUPPORTED; }
+    const int smem = 1024 + a.stages * stage_bytes + 512;
     const int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
     cudaError_t ce = cudaSuccess;
 #define VS_GEMM_TC(E, L)                                                                                   \

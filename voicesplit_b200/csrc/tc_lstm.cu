@@ -36,8 +36,12 @@ struct LstmTcArgs {
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
-    // 1 / (1 + 2^(-x log2 e)): ex2.approx + rcp.approx, relative error ~2^-22
-    return __frcp_rn(1.f + exp2f(-1.4426950408889634f * x));
+    // 1 / (1 + 2^(-x log2 e)) with the raw MUFU approximations (no range/denormal slow paths):
+    // ex2.approx and rcp.approx are each accurate to ~2^-22 relative
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
 }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
 
@@ -234,8 +238,9 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 }
             }
             if (s + 1 < a.T) {
-                // publish h_s: all 128 cell threads have stored, then one of them releases the counter
-                __threadfence();
+                // publish h_s: the 128 cell threads meet at a CTA barrier, then ONE thread issues the
+                // gpu-scope release (cumulative over the stores ordered before the barrier) and bumps
+                // the counter - the cooperative-groups grid-sync pattern, without a fence per thread
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (threadIdx.x == 64) {
                     __threadfence();
