@@ -236,10 +236,33 @@ def main():
     launches_per_step = eng.last_launch_count()
     eng.set_profiling(False)
     value, dev_ms = vdist.aggregate_throughput(B * args.steps, local_ms, dist, dev)
-    # ---- end to end through the host-buffer plugin call ("e2e"): H2D + forward + D2H every step
+    # ---- end to end through the host-buffer plugin call ("e2e"): every step copies its inputs from pinned
+    # host memory, runs the forward and copies mask + masked back.  The serving form of the call is
+    # used (vs_forward_host_submit / _wait, two slots), so the copies of step i+1 / i-1 overlap the
+    # compute of step i; the synchronous vs_forward_host is timed as well and reported next to it.
     for _ in range(min(args.warmup, 2)):
         eng.forward_host(xh, eh, mask_h, masked_h, precision=prec)
-    local_e2e = timed(lambda: eng.forward_host(xh, eh, mask_h, masked_h, precision=prec), args.steps)
+    local_sync = timed(lambda: eng.forward_host(xh, eh, mask_h, masked_h, precision=prec), max(2, args.steps // 2))
+    sync_value, _ = vdist.aggregate_throughput(B * max(2, args.steps // 2), local_sync, dist, dev)
+    slots = [(xh, eh, mask_h, masked_h),
+             (xh.clone().pin_memory(), eh.clone().pin_memory(), torch.empty_like(xh).pin_memory(), torch.empty_like(xh).pin_memory())]
+
+    def pipelined(steps):
+        for i in range(steps):
+            eng.host_submit(i & 1, *slots[i & 1], precision=prec)
+            if i > 0:
+                eng.host_wait((i - 1) & 1)
+        eng.host_wait((steps - 1) & 1)
+
+    pipelined(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pipelined(args.steps)           # the last host_wait blocks until the last D2H has landed
+    e1.record()
+    torch.cuda.synchronize()
+    local_e2e = e0.elapsed_time(e1)
+    barrier()
     e2e_value, e2e_ms = vdist.aggregate_throughput(B * args.steps, local_e2e, dist, dev)
     clocks = sampler.stop() if rank == 0 else None
     # ---- the single-pass fast mode, reported next to its measured error (never as the headline)
@@ -289,6 +312,8 @@ def main():
                           "bf16": "bf16", "fp16": "f16", "fp32": "f32"}[prec],
                 "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "utterances/s", "ms_per_step": e2e_ms / args.steps,
+                        "api": "vs_forward_host_submit/_wait (2 slots, copies overlap the neighbouring step's compute)",
+                        "synchronous_call_value": sync_value,
                         "h2d_bytes_per_step": int(xh.numel() * 4 + eh.numel() * 4),
                         "d2h_bytes_per_step": int(mask_h.numel() * 4 + masked_h.numel() * 4)},
                 "gpu_launches": launches_per_step * args.steps * 2,   # device-resident + e2e timed regions

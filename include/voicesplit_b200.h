@@ -118,6 +118,16 @@ int vs_forward(vs_engine* e, const float* x, const float* emb, float* mask, floa
 int vs_forward_host(vs_engine* e, const float* x_host, const float* emb_host, float* mask_host,
                     float* masked_host, int32_t B, int32_t T, int32_t precision, void* stream);
 
+/* Pipelined form of vs_forward_host for serving loops: two slots (0, 1), each with its own device
+ * staging.  submit enqueues  H2D (copy stream) -> vs_forward (compute stream) -> D2H (copy stream)
+ * for one batch and returns immediately; wait blocks until that slot's outputs are in host memory.
+ * Submitting slot s while slot 1-s is in flight overlaps its copies with the other slot's compute.
+ * Host buffers must be pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous,
+ * and must not be touched between submit and wait.  A slot must be waited on before it is reused. */
+int vs_forward_host_submit(vs_engine* e, int32_t slot, const float* x_host, const float* emb_host,
+                           float* mask_host, float* masked_host, int32_t B, int32_t T, int32_t precision);
+int vs_forward_host_wait(vs_engine* e, int32_t slot);
+
 /* Conv stack only (reference model.conv + the transpose/view of model.py:70-74):
  * x [B][T][F] -> conv_out [B][T][8F] fp32 device (index c*F+f). */
 int vs_conv_stack(vs_engine* e, const float* x, float* conv_out, int32_t B, int32_t T,

@@ -199,3 +199,48 @@ def test_fp16_modes_stay_finite_on_huge_activations():
     for p in ("fp16x3", "fp16"):
         assert torch.isfinite(eng.forward(xt, et, precision=p)).all()
     assert (eng.forward(xt, et, precision="bf16x3") - ref).abs().max() < 1e-3
+
+
+def test_many_utterance_groups_lstm_multi_launch():
+    """More 128-utterance groups than are co-resident (H=400: 2 groups per launch) -> the recurrent kernel
+    is launched per chunk of groups; every utterance must still equal its stand-alone result."""
+    dims = synth.make_dims(17, 8, 400, 24)
+    sd = synth.make_state_dict(dims, 12, "stress")
+    eng = MaskEngine(activation="mish", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    x, emb = synth.make_inputs(300, 6, dims, 8)
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
+    full = eng.forward(xt, et, precision="fp16x3")
+    ref = eng.forward(xt, et, precision="fp32")
+    assert (full - ref).abs().max() < 1e-3
+    for b in (0, 127, 128, 257, 299):
+        one = eng.forward(xt[b:b + 1], et[b:b + 1], precision="fp16x3")
+        assert torch.allclose(full[b:b + 1], one, atol=2e-6, rtol=0), b
+
+
+def test_pipelined_host_entry_matches_synchronous():
+    dims = synth.make_dims(33, 16, 24, 40)
+    sd = synth.make_state_dict(dims, 2, "stress")
+    eng = MaskEngine(activation="mish", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    bufs = []
+    for i in range(2):
+        x, emb = synth.make_inputs(3, 21 + 5 * i, dims, 40 + i)
+        x, emb = torch.from_numpy(x).pin_memory(), torch.from_numpy(emb).pin_memory()
+        bufs.append((x, emb, torch.empty_like(x).pin_memory(), torch.empty_like(x).pin_memory()))
+    want = []
+    for x, emb, _, _ in bufs:
+        m = torch.empty_like(x).pin_memory(); mm = torch.empty_like(x).pin_memory()
+        eng.forward_host(x, emb, m, mm, precision="fp16x3")
+        want.append((m.clone(), mm.clone()))
+    for rounds in range(3):                     # reuse the slots several times, both in flight at once
+        eng.host_submit(0, *bufs[0], precision="fp16x3")
+        eng.host_submit(1, *bufs[1], precision="fp16x3")
+        with pytest.raises(Exception, match="in flight"):
+            eng.host_submit(1, *bufs[1], precision="fp16x3")
+        eng.host_wait(0); eng.host_wait(1)
+        for i in range(2):
+            assert torch.equal(bufs[i][2], want[i][0]) and torch.equal(bufs[i][3], want[i][1])
+            bufs[i][2].zero_(); bufs[i][3].zero_()
+    with pytest.raises(Exception, match="nothing submitted"):
+        eng.host_wait(0)

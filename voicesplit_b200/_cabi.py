@@ -42,6 +42,8 @@ SIGNATURES = {
     "vs_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
     "vs_forward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_forward_host": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "vs_forward_host_submit": (ctypes.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I]),
+    "vs_forward_host_wait": (ctypes.c_int, [_VP, _I]),
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),

@@ -106,6 +106,8 @@ struct vs_engine {
     // host staging for vs_forward_host (grow-only)
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    // pipelined host entry (vs_forward_host_submit / _wait): HostPipe in engine.cu
+    void* pipe = nullptr;
 
     // tensor-core path state (tc_*.cu)
     void* tc = nullptr;

@@ -130,9 +130,10 @@ static int check_common(const vs_engine* e, int B, int T, int precision) {
     if (precision < VS_PREC_FP32 || precision > VS_PREC_FP16) {
         set_error("unknown precision"); return VS_ERR_INVALID;
     }
-    if ((long long)B * T * padded_freq(e->d.num_freq) >= (1LL << 31) / 64) {
-        // pixel indices are kept in 32 bits inside the kernels' tile schedulers
-        if ((long long)B * T * padded_freq(e->d.num_freq) >= (1LL << 31)) { set_error("batch too large"); return VS_ERR_INVALID; }
+    // the kernels' tile schedulers keep tile and row indices in 32 bits
+    if ((long long)B * T * padded_freq(e->d.num_freq) >= (1LL << 31)) { set_error("batch too large: B*T*Fp must be < 2^31"); return VS_ERR_INVALID; }
+    if (precision != VS_PREC_FP32 && (e->d.lstm_dim % 4) != 0) {
+        set_error("tensor-core precisions need lstm_dim % 4 == 0 (16-byte operand rows); use VS_PREC_FP32"); return VS_ERR_INVALID;
     }
     return VS_OK;
 }
@@ -174,6 +175,8 @@ using namespace vs;
 
 extern "C" {
 
+static void pipe_destroy(vs_engine* e);  // pipelined host entry, defined below
+
 int vs_abi_version(void) { return VS_ABI_VERSION; }
 const char* vs_last_error(void) { return g_err.c_str(); }
 
@@ -213,6 +216,7 @@ int vs_engine_create(const vs_dims* dims, vs_engine** out) {
 
 int vs_engine_destroy(vs_engine* e) {
     if (!e) return VS_OK;
+    pipe_destroy(e);
     free_params(e);
     tc_destroy(e);
     if (e->prof) {
@@ -335,6 +339,103 @@ int vs_forward_host(vs_engine* e, const float* x_host, const float* emb_host, fl
     VS_CUDA_TRY(cudaMemcpyAsync(mask_host, dmask, nx, cudaMemcpyDeviceToHost, st));
     if (masked_host) VS_CUDA_TRY(cudaMemcpyAsync(masked_host, dmasked, nx, cudaMemcpyDeviceToHost, st));
     VS_CUDA_TRY(cudaStreamSynchronize(st));
+    return VS_OK;
+}
+
+// ---- pipelined host entry --------------------------------------------------------------------
+struct HostSlot {
+    void* io = nullptr;       // device staging: x, emb, mask, masked
+    size_t io_bytes = 0;
+    cudaEvent_t h2d = nullptr, fwd = nullptr, done = nullptr;
+    bool busy = false;
+};
+struct HostPipe {
+    cudaStream_t copy_in = nullptr, compute = nullptr, copy_out = nullptr;
+    void* ws = nullptr;       // one workspace: forwards of the two slots are serialised on `compute`
+    size_t ws_bytes = 0;
+    HostSlot slot[2];
+};
+
+static int pipe_get(vs_engine* e, HostPipe** out) {
+    if (!e->pipe) {
+        HostPipe* p = new (std::nothrow) HostPipe();
+        if (!p) { set_error("out of host memory"); return VS_ERR_STATE; }
+        VS_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
+        VS_CUDA_TRY(cudaStreamCreateWithFlags(&p->compute, cudaStreamNonBlocking));
+        VS_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
+        for (HostSlot& s : p->slot) {
+            VS_CUDA_TRY(cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming));
+            VS_CUDA_TRY(cudaEventCreateWithFlags(&s.fwd, cudaEventDisableTiming));
+            VS_CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        e->pipe = p;
+    }
+    *out = (HostPipe*)e->pipe;
+    return VS_OK;
+}
+
+static void pipe_destroy(vs_engine* e) {
+    HostPipe* p = (HostPipe*)e->pipe;
+    if (!p) return;
+    cudaStreamSynchronize(p->copy_in); cudaStreamSynchronize(p->compute); cudaStreamSynchronize(p->copy_out);
+    for (HostSlot& s : p->slot) { cudaFree(s.io); cudaEventDestroy(s.h2d); cudaEventDestroy(s.fwd); cudaEventDestroy(s.done); }
+    cudaFree(p->ws);
+    cudaStreamDestroy(p->copy_in); cudaStreamDestroy(p->compute); cudaStreamDestroy(p->copy_out);
+    delete p;
+    e->pipe = nullptr;
+}
+
+int vs_forward_host_submit(vs_engine* e, int32_t slot, const float* x_host, const float* emb_host, float* mask_host,
+                           float* masked_host, int32_t B, int32_t T, int32_t precision) {
+    int rc = check_common(e, B, T, precision);
+    if (rc != VS_OK) return rc;
+    if (slot < 0 || slot > 1) { set_error("slot must be 0 or 1"); return VS_ERR_INVALID; }
+    if (!x_host || !emb_host || !mask_host) { set_error("null buffer"); return VS_ERR_INVALID; }
+    HostPipe* p = nullptr;
+    rc = pipe_get(e, &p);
+    if (rc != VS_OK) return rc;
+    HostSlot& s = p->slot[slot];
+    if (s.busy) { set_error("slot still in flight: call vs_forward_host_wait first"); return VS_ERR_STATE; }
+    const size_t nx = (size_t)B * T * e->d.num_freq * sizeof(float), ne = (size_t)B * e->d.emb_dim * sizeof(float);
+    const size_t io_need = align_up(nx, 1024) * 3 + align_up(ne, 1024);
+    const size_t wsb = vs_workspace_bytes(e, B, T, precision);
+    if (io_need > s.io_bytes) {     // grow-only; steady-state calls of one shape never allocate
+        cudaFree(s.io); s.io = nullptr; s.io_bytes = 0;
+        VS_CUDA_TRY(cudaMalloc(&s.io, io_need));
+        s.io_bytes = io_need;
+    }
+    if (wsb > p->ws_bytes) {
+        VS_CUDA_TRY(cudaStreamSynchronize(p->compute));
+        cudaFree(p->ws); p->ws = nullptr; p->ws_bytes = 0;
+        VS_CUDA_TRY(cudaMalloc(&p->ws, wsb));
+        p->ws_bytes = wsb;
+    }
+    char* q = (char*)s.io;
+    float* dx = (float*)q; q += align_up(nx, 1024);
+    float* dmask = (float*)q; q += align_up(nx, 1024);
+    float* dmasked = (float*)q; q += align_up(nx, 1024);
+    float* demb = (float*)q;
+    VS_CUDA_TRY(cudaMemcpyAsync(dx, x_host, nx, cudaMemcpyHostToDevice, p->copy_in));
+    VS_CUDA_TRY(cudaMemcpyAsync(demb, emb_host, ne, cudaMemcpyHostToDevice, p->copy_in));
+    VS_CUDA_TRY(cudaEventRecord(s.h2d, p->copy_in));
+    VS_CUDA_TRY(cudaStreamWaitEvent(p->compute, s.h2d, 0));
+    rc = vs_forward(e, dx, demb, dmask, masked_host ? dmasked : nullptr, B, T, precision, p->ws, p->ws_bytes, p->compute);
+    if (rc != VS_OK) return rc;
+    VS_CUDA_TRY(cudaEventRecord(s.fwd, p->compute));
+    VS_CUDA_TRY(cudaStreamWaitEvent(p->copy_out, s.fwd, 0));
+    VS_CUDA_TRY(cudaMemcpyAsync(mask_host, dmask, nx, cudaMemcpyDeviceToHost, p->copy_out));
+    if (masked_host) VS_CUDA_TRY(cudaMemcpyAsync(masked_host, dmasked, nx, cudaMemcpyDeviceToHost, p->copy_out));
+    VS_CUDA_TRY(cudaEventRecord(s.done, p->copy_out));
+    s.busy = true;
+    return VS_OK;
+}
+
+int vs_forward_host_wait(vs_engine* e, int32_t slot) {
+    if (!e || !e->pipe || slot < 0 || slot > 1) { set_error("nothing submitted on this slot"); return VS_ERR_STATE; }
+    HostSlot& s = ((HostPipe*)e->pipe)->slot[slot];
+    if (!s.busy) { set_error("nothing submitted on this slot"); return VS_ERR_STATE; }
+    VS_CUDA_TRY(cudaEventSynchronize(s.done));
+    s.busy = false;
     return VS_OK;
 }
 

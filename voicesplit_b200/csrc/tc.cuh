@@ -36,8 +36,8 @@ size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision);
 // Everything after the 64-channel conv planes: cnn8 (+reshape), LSTM, head.  If conv_out32 is given
 // the planes are ignored and the LSTM input is taken from it (debug hook).
 int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32,
-                 const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, float* xcat32,
-                 float* fc1, void* gemm_ws, const TcLstmBuffers& lb, cudaStream_t st);
+                 const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, void* gemm_ws,
+                 const TcLstmBuffers& lb, cudaStream_t st);
 // ---- tc_lstm.cu: tensor-core recurrent kernel ---------------------------------------------------
 int tc_lstm_pack(vs_engine* e, void** slot, cudaStream_t st);
 void tc_lstm_destroy(void* slot);

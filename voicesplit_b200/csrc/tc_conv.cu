@@ -567,9 +567,7 @@ static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const e
 // ---- workspace of the tensor-core path ---------------------------------------------------------
 struct TcWorkspace {
     elt16 *a_hi, *a_lo, *b_hi, *b_lo;  // ping-pong activation planes
-    float* xcat32;                              // [B*T][8F]
-    float* fc1;                                 // [B*T][fc1]
-    void* gemm;                                 // operands of the tensor-core GEMMs
+    void* gemm;                         // operands of the tensor-core GEMMs
     size_t total;
 };
 static TcWorkspace tc_carve(const vs_engine* e, int B, int T, int precision, void* base) {
@@ -585,8 +583,6 @@ static TcWorkspace tc_carve(const vs_engine* e, int B, int T, int precision, voi
         w.a_lo = (elt16*)take(plane);
         w.b_lo = (elt16*)take(plane);
     }
-    w.xcat32 = (float*)take((size_t)B * T * 8 * F * sizeof(float));
-    w.fc1 = (float*)take((size_t)B * T * e->d.fc1_dim * sizeof(float));
     w.gemm = take(tc_gemm_workspace_bytes(e, B, T, precision));
     w.total = off;
     return w;
@@ -624,7 +620,7 @@ int tc_forward(vs_engine* e, const float* x, const float* emb, float* mask, floa
     elt16 *rh, *rl;
     int rc = conv_layers_tc(e, x, w, B, T, precision, st, &rh, &rl);
     if (rc != VS_OK) return rc;
-    return tc_lstm_head(e, rh, rl, nullptr, emb, x, mask, masked, B, T, precision, w.xcat32, w.fc1, w.gemm, lb, st);
+    return tc_lstm_head(e, rh, rl, nullptr, emb, x, mask, masked, B, T, precision, w.gemm, lb, st);
 }
 
 int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_in, float* plane_out, int B, int T,

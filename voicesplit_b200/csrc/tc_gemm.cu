@@ -337,9 +337,8 @@ static int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, con
 }
 
 int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32, const float* emb,
-                 const float* x, float* mask, float* masked, int B, int T, int precision, float* xcat32, float* fc1, void* gemm_ws,
+                 const float* x, float* mask, float* masked, int B, int T, int precision, void* gemm_ws,
                  const TcLstmBuffers& lb, cudaStream_t st) {
-    (void)xcat32; (void)fc1;
     GemmState* g = g_state(e);
     const int F = e->d.num_freq, H = e->d.lstm_dim, E = e->d.emb_dim, N1 = e->d.fc1_dim;
     const int M = B * T, elt = tc_elt(precision);
@@ -385,7 +384,7 @@ int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, co
                        int precision, const TcLstmBuffers& lb, cudaStream_t st) {
     void* ws = nullptr;
     VS_CUDA_TRY(cudaMalloc(&ws, tc_gemm_workspace_bytes(e, B, T, precision)));
-    int rc = tc_lstm_head(e, nullptr, nullptr, conv_out, emb, x, mask, nullptr, B, T, precision, nullptr, nullptr, ws, lb, st);
+    int rc = tc_lstm_head(e, nullptr, nullptr, conv_out, emb, x, mask, nullptr, B, T, precision, ws, lb, st);
     cudaStreamSynchronize(st);
     cudaFree(ws);
     return rc;

@@ -121,6 +121,17 @@ class MaskEngine:
                         "vs_forward_host")
         return mask_host
 
+    def host_submit(self, slot, x_host, emb_host, mask_host, masked_host=None, precision="fp16x3"):
+        """Pipelined host entry: enqueue H2D -> forward -> D2H for one batch on `slot` (0 or 1)."""
+        B, T, _ = x_host.shape
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.vs_forward_host_submit(self.handle, slot, _ptr(x_host), _ptr(emb_host), _ptr(mask_host),
+                                                        _ptr(masked_host), B, T, self._prec(precision)), "vs_forward_host_submit")
+
+    def host_wait(self, slot):
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.vs_forward_host_wait(self.handle, slot), "vs_forward_host_wait")
+
     def conv_stack(self, x, precision="fp16x3"):
         x = x.detach().to(torch.float32).contiguous()
         B, T, F = x.shape
