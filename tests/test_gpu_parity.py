@@ -64,12 +64,11 @@ def test_lstm_and_head_match_golden(golden, precision):
     conv = torch.from_numpy(golden["conv_out"]).cuda()
     lstm_out, mask = eng.debug_lstm_head(conv, torch.from_numpy(golden["emb"]).cuda(),
                                          torch.from_numpy(golden["x"]).cuda(), precision=precision)
-    # intermediate check: the tensor-core modes sum K = 8F (up to 4808) products per gate in TMEM, whose
-    # fp32 accumulation order differs from the reference's; with the x4 stress LSTM weights a single
-    # gate output can move by ~1.2e-3 (measured, same for fp16x3 and bf16x3, tools/diag_lstm.py) while the
-    # mask - the quantity with the 1e-3 bar - stays within 4e-4
+    # tcgen05 accumulates into TMEM with truncation (tools/umma_probe.cu: ~0.3 ulp per step, toward zero);
+    # the GEMM promotes partial sums to fp32 registers every 8 K-blocks, which keeps the K = 8F = 4808
+    # input projection within this bound even with the x4 stress LSTM weights
     d = np.abs(lstm_out.cpu().numpy() - golden["lstm_out"])
-    assert d.max() < (1e-3 if precision == "fp32" else 2e-3) and d.mean() < 2e-5
+    assert d.max() < 1e-3 and d.mean() < 1e-5
     assert np.abs(mask.cpu().numpy() - golden["mask"]).max() < 1e-3
 
 

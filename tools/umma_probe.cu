@@ -203,6 +203,29 @@ int main() {
         CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
         printf("PROBE %-32s cycles_per_mma=%.1f (ideal %d)\n", t.name, (double)cyc / (2000.0 * 4), t.N / 2);
     }
+    // accumulation behaviour: repeat the same K=64 product `it` times into one TMEM accumulator and compare
+    // with it * (exact product): round-to-nearest accumulation errs like sqrt(steps) ulp with random sign,
+    // truncation errs like 0.5 * steps ulp, always toward zero
+    for (int iters : {1, 16, 64, 256, 1024}) {
+        ProbeArgs a{dA, dB, dD, 64, strip, 0, 2, 0, 0, iters, dcyc};
+        probe_kernel<<<1, 128, smem_bytes>>>(a, tmA, tmB);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hD.data(), dD, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+        double rel_sum = 0, rel_max = 0, toward_zero = 0;
+        int cnt = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < 64; ++n) {
+                double s = 0;
+                for (int k = 0; k < 64; ++k) s += (double)hA[m * 64 + k] * hB[n * 64 + k];
+                double want = s * iters, got = hD[m * 64 + n];
+                if (fabs(want) < 1.0) continue;
+                double rel = (got - want) / want;       // negative = magnitude too small = toward zero
+                rel_sum += rel; if (fabs(rel) > rel_max) rel_max = fabs(rel);
+                toward_zero += rel < 0; ++cnt;
+            }
+        printf("PROBE accumulate_x%-5d mma_steps=%-5d mean_rel_err=%+.3e max_rel_err=%.3e frac_toward_zero=%.2f\n", iters, iters * 4,
+               rel_sum / cnt, rel_max, toward_zero / cnt);
+    }
     printf("PROBE done\n");
     return 0;
 }

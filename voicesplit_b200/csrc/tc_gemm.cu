@@ -10,6 +10,13 @@
 // N tails, so nothing is padded in memory.  In the 3-pass modes one pipeline stage holds all four
 // operand tiles of a K block (A_hi, A_lo, W_hi, W_lo: each fetched once) and the issuer runs
 // hi*hi + lo*hi + hi*lo on it.  Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.
+//
+// Accumulation: tcgen05 adds into the fp32 TMEM accumulator with truncation (measured with
+// tools/umma_probe.cu: ~0.3 ulp per accumulate step, always toward zero - profiles/r01_umma_probe.txt),
+// which over the K = 8F = 4808 input projection (912 steps in 3-pass mode) is a -1.7e-5 relative bias.
+// So the K loop is cut into chunks of kChunkKb K-blocks: each chunk accumulates in one of the two TMEM
+// buffers and the epilogue warps add the chunk into fp32 registers (round-to-nearest) while the
+// next chunk runs in the other buffer - the "promotion" FP8 GEMMs use, for the same reason.
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
 
@@ -17,6 +24,7 @@ namespace vs {
 using namespace ptx;
 
 constexpr int kGemmEpiWarps = 8;
+constexpr int kChunkKb = 8;        // K blocks (of 64) accumulated in TMEM before promotion to registers
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2 };
 
@@ -92,51 +100,77 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, a.n_tile, ELT);
-            int st = 0, ph = 0, it = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&acc_empty[buf], aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem + (uint32_t)(buf * 256);
-                uint32_t accumulate = 0;
-                for (int kb = 0; kb < a.n_kb; ++kb) {
-                    mbar_wait(&full[st], ph);
+            int st = 0, ph = 0, cc = 0;   // cc: chunk counter across tiles (TMEM buffer = cc & 1)
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                for (int kb0 = 0; kb0 < a.n_kb; kb0 += kChunkKb, ++cc) {
+                    const int buf = cc & 1, aph = (cc >> 1) & 1;
+                    mbar_wait(&acc_empty[buf], aph ^ 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)st * stage_bytes), a_lo = a_hi + a_bytes;
-                    const uint32_t w_hi = a_hi + nplanes * a_bytes, w_lo = w_hi + w_bytes_al;
+                    const uint32_t d_tmem = tmem + (uint32_t)(buf * 256);
+                    uint32_t accumulate = 0;
+                    const int kb1 = kb0 + kChunkKb < a.n_kb ? kb0 + kChunkKb : a.n_kb;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(smem + (size_t)st * stage_bytes), a_lo = a_hi + a_bytes;
+                        const uint32_t w_hi = a_hi + nplanes * a_bytes, w_lo = w_hi + w_bytes_al;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
-                        accumulate = 1;
-                        if (nplanes == 2) {
-                            umma_bf16(d_tmem, make_smem_desc(a_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
-                            umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
+                            accumulate = 1;
+                            if (nplanes == 2) {
+                                umma_bf16(d_tmem, make_smem_desc(a_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
+                                umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
+                            }
                         }
+                        umma_commit(&empty[st]);
+                        if (++st == nst) { st = 0; ph ^= 1; }
                     }
-                    umma_commit(&empty[st]);
-                    if (++st == nst) { st = 0; ph ^= 1; }
+                    umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&acc_full[buf]);
             }
         }
     } else {
         // epilogue: thread = one row of A (TMEM lane); warps of a quadrant alternate 32-column chunks
         const int quad = warp & 3, cgrp = (warp - 2) >> 2;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1, aph = (it >> 1) & 1;
+        constexpr int kColStep = 32 * (kGemmEpiWarps / 4);      // this warp takes columns cgrp*32 + i*kColStep .. +32
+        constexpr int kMaxCols = 256 / kColStep;                // at most 4 column chunks per warp
+        int cc = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
             const int m = mb * 128 + quad * 32 + lane;
             const int n0 = nb * a.n_tile;
-            mbar_wait(&acc_full[buf], aph);
-            tc_fence_after();
-            const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
-            const float* bg = (EPI == GEPI_GATES && m < a.M) ? a.bias_group + (size_t)(m / a.group_rows) * a.N : nullptr;
-            for (int c0 = cgrp * 32; c0 < a.n_tile; c0 += 32 * (kGemmEpiWarps / 4)) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_base + c0, r);
-                tmem_ld_wait();
-                if (m < a.M) {
+            float acc[kMaxCols][32];
+#pragma unroll
+            for (int i = 0; i < kMaxCols; ++i)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[i][j] = 0.f;
+            for (int kb0 = 0; kb0 < a.n_kb; kb0 += kChunkKb, ++cc) {
+                const int buf = cc & 1, aph = (cc >> 1) & 1;
+                mbar_wait(&acc_full[buf], aph);
+                tc_fence_after();
+                const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
+#pragma unroll
+                for (int i = 0; i < kMaxCols; ++i) {
+                    const int c0 = cgrp * 32 + i * kColStep;
+                    if (c0 < a.n_tile) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_base + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[i][j] += __uint_as_float(r[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            if (m < a.M) {
+                const float* bg = (EPI == GEPI_GATES) ? a.bias_group + (size_t)(m / a.group_rows) * a.N : nullptr;
+#pragma unroll
+                for (int i = 0; i < kMaxCols; ++i) {
+                    const int c0 = cgrp * 32 + i * kColStep;
+                    if (c0 >= a.n_tile) continue;
                     const int nbase = n0 + c0;
                     if (EPI == GEPI_GATES) {
                         float* dst = a.out32 + (size_t)m * a.ld_out + nbase;
@@ -144,19 +178,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 float4 b4 = *reinterpret_cast<const float4*>(bg + nbase + j);
-                                float4 o = make_float4(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
-                                                       __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w);
-                                *reinterpret_cast<float4*>(dst + j) = o;
+                                *reinterpret_cast<float4*>(dst + j) =
+                                    make_float4(acc[i][j] + b4.x, acc[i][j + 1] + b4.y, acc[i][j + 2] + b4.z, acc[i][j + 3] + b4.w);
                             }
                         } else {
-                            for (int j = 0; j < 32 && nbase + j < a.N && c0 + j < a.n_tile; ++j) dst[j] = __uint_as_float(r[j]) + bg[nbase + j];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nbase + j < a.N && c0 + j < a.n_tile) dst[j] = acc[i][j] + bg[nbase + j];
                         }
                     } else if (EPI == GEPI_FC1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n = nbase + j;
                             if (n < a.N && c0 + j < a.n_tile) {
-                                float v = fmaxf(__uint_as_float(r[j]) + a.bias[n], 0.f);
+                                float v = fmaxf(acc[i][j] + a.bias[n], 0.f);
                                 elt16 vh, vl;
                                 split16<ELT>(v, vh, vl);
                                 a.out_hi[(size_t)m * a.ld16 + n] = vh;
@@ -168,7 +203,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                         for (int j = 0; j < 32; ++j) {
                             const int n = nbase + j;
                             if (n < a.N && c0 + j < a.n_tile) {
-                                float v = sigmoid_f(__uint_as_float(r[j]) + a.bias[n]);
+                                float v = sigmoid_f(acc[i][j] + a.bias[n]);
                                 const size_t o = (size_t)m * a.ld_out + n;
                                 a.out32[o] = v;
                                 if (a.masked) a.masked[o] = a.xmul[o] * v;
@@ -177,9 +212,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();
