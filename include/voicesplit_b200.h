@@ -133,6 +133,42 @@ int vs_forward_host_wait(vs_engine* e, int32_t slot);
 int vs_conv_stack(vs_engine* e, const float* x, float* conv_out, int32_t B, int32_t T,
                   int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training (BASELINE config 4): fp32, BatchNorm with batch statistics, full backward -------------
+ * vs_train_forward is VoiceSplit.forward in .train() mode (models/voicesplit/model.py:66-89 under
+ * train.py:84,94): every BatchNorm normalises with the statistics of this batch and, when `bn` is
+ * given, updates running_mean / running_var (momentum, unbiased variance) and num_batches_tracked in
+ * place - the tensors of the module's own buffers.  It keeps what the backward needs in `workspace`
+ * (vs_train_workspace_bytes), which must stay untouched until vs_train_backward has run.
+ * vs_train_backward consumes d(loss)/d(mask) and writes the gradient of every parameter in the
+ * reference's layouts (vs_grads mirrors vs_params) plus, optionally, d(loss)/d(emb).  Parameters must
+ * have been loaded with vs_engine_load_params since their last change. */
+typedef struct vs_train_state {
+    float* running_mean[8];
+    float* running_var[8];
+    int64_t* num_batches_tracked[8];
+    float momentum; /* nn.BatchNorm2d default 0.1 */
+} vs_train_state;
+typedef struct vs_grads {
+    float* conv_w[8];
+    float* conv_b[8];
+    float* bn_gamma[8];
+    float* bn_beta[8];
+    float* w_ih[2];
+    float* w_hh[2];
+    float* b_ih[2];
+    float* b_hh[2];
+    float* fc1_w;
+    float* fc1_b;
+    float* fc2_w;
+    float* fc2_b;
+} vs_grads;
+size_t vs_train_workspace_bytes(const vs_engine* e, int32_t B, int32_t T);
+int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, const float* emb, float* mask,
+                     int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream);
+int vs_train_backward(vs_engine* e, const float* x, const float* emb, const float* mask, const float* grad_mask,
+                      const vs_grads* grads, float* grad_emb, int32_t B, int32_t T, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Test hooks: run a single conv layer l (0..6 -> 64-channel output) on an fp32 NCHW input
  * in [B][Cin][T][F] -> out [B][64][T][F], and the BiLSTM + head on a given conv_out.
  * They allocate internally and synchronise; not for the hot path. */

@@ -56,3 +56,28 @@ def forward(sd, x, emb, activation="mish"):
     y = F.linear(torch.relu(out), _t(sd, "fc1.weight"), _t(sd, "fc1.bias"))
     y = F.linear(torch.relu(y), _t(sd, "fc2.weight"), _t(sd, "fc2.bias"))
     return torch.sigmoid(y)
+
+
+def forward_train(sd, x, emb, activation="mish", momentum=0.1):
+    """Training-mode forward with autograd (BatchNorm batch statistics, running-stat update in place on
+    the tensors of `sd`), the way train.py:84,94 drives the reference module.  `sd` maps the reference
+    state_dict keys to torch tensors; parameters that should receive .grad must have requires_grad=True."""
+    B, T, _ = x.shape
+    h = x.unsqueeze(1)
+    for ci, bi, pad, dil in _CONVS:
+        if pad is not None:
+            h = F.pad(h, pad)
+        h = F.conv2d(h, sd[f"conv.{ci}.weight"], sd[f"conv.{ci}.bias"], dilation=(dil, 1))
+        h = F.batch_norm(h, sd[f"conv.{bi}.running_mean"], sd[f"conv.{bi}.running_var"], sd[f"conv.{bi}.weight"],
+                         sd[f"conv.{bi}.bias"], training=True, momentum=momentum, eps=1e-5)
+        sd[f"conv.{bi}.num_batches_tracked"] += 1
+        h = _act(h, activation)
+    Bq, C, Tq, Fq = h.shape
+    feat = torch.cat((h.permute(0, 2, 1, 3).reshape(B, T, C * Fq), emb[:, None, :].expand(B, T, emb.shape[1])), dim=2)
+    H = sd["lstm.weight_hh_l0"].shape[1]
+    flat = [sd[f"lstm.{n}_l0{s}"] for s in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    zeros = torch.zeros(2, B, H)
+    out, _, _ = torch._VF.lstm(feat, (zeros, zeros), flat, True, 1, 0.0, True, True, True)
+    y = F.linear(torch.relu(out), sd["fc1.weight"], sd["fc1.bias"])
+    y = F.linear(torch.relu(y), sd["fc2.weight"], sd["fc2.bias"])
+    return torch.sigmoid(y)

@@ -31,6 +31,17 @@ class VsParams(ctypes.Structure):
                [(n, ctypes.c_void_p) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class VsTrainState(ctypes.Structure):
+    _fields_ = [("running_mean", ctypes.c_void_p * 8), ("running_var", ctypes.c_void_p * 8),
+                ("num_batches_tracked", ctypes.c_void_p * 8), ("momentum", ctypes.c_float)]
+
+
+class VsGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * 8) for n in ("conv_w", "conv_b", "bn_gamma", "bn_beta")] + \
+               [(n, ctypes.c_void_p * 2) for n in ("w_ih", "w_hh", "b_ih", "b_hh")] + \
+               [(n, ctypes.c_void_p) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
 # name -> (restype, argtypes); must list every function include/voicesplit_b200.h declares
 _VP, _I, _SZ = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
 SIGNATURES = {
@@ -44,6 +55,9 @@ SIGNATURES = {
     "vs_forward_host": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "vs_forward_host_submit": (ctypes.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I]),
     "vs_forward_host_wait": (ctypes.c_int, [_VP, _I]),
+    "vs_train_workspace_bytes": (_SZ, [_VP, _I, _I]),
+    "vs_train_forward": (ctypes.c_int, [_VP, ctypes.POINTER(VsTrainState), _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_train_backward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, ctypes.POINTER(VsGrads), _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),

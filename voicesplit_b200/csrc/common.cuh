@@ -41,6 +41,7 @@ __device__ __forceinline__ float mish_precise(float x) {
 }
 template <int ACT>
 __device__ __forceinline__ float activate(float x) {
+    if (ACT == 2) return x;                       // VS_ACT_NONE (train.cuh): raw pre-BatchNorm output
     if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
     return mish_precise(x);
 }
@@ -102,6 +103,12 @@ struct vs_engine {
     float* b_lstm = nullptr;    // fp32 [8H]       b_ih + b_hh
     float* whh = nullptr;       // fp32 [2][4H][H]
     float* fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;
+    // training path: data-gradient conv weights [tap'][co][ci] (layers 1..6), raw per-channel vectors
+    float* conv_wT32[8] = {};
+    float* conv_bias[8] = {};   // conv bias (not folded)
+    float* bn_gamma[8] = {};
+    float* bn_beta[8] = {};
+    float* ones64 = nullptr, *zeros64 = nullptr;
 
     // host staging for vs_forward_host (grow-only)
     void* stage = nullptr;
@@ -137,6 +144,10 @@ void prof_after(vs_engine* e, int id, cudaStream_t st);
         if ((e)->profiling) vs::prof_after((e), (id), (st));                                   \
     } while (0)
 
+// training path (train.cu): raw per-channel vectors + data-gradient weights, refreshed by vs_engine_load_params
+int train_pack(vs_engine* e, const vs_params* p, cudaStream_t st);
+void train_free(vs_engine* e);
+
 // fp32 kernels (fp32_kernels.cu); all launch on `st` and return a cudaError_t
 cudaError_t launch_front_fp32(const vs_engine* e, const float* x, float* plane, int B, int T, cudaStream_t st);
 cudaError_t launch_conv_fp32(const vs_engine* e, int layer, const float* in, float* out, int B, int T, cudaStream_t st);
@@ -147,9 +158,10 @@ cudaError_t launch_gemm_fp32(const float* A, int lda, const float* W, int ldw, c
                              const float* bias_group, int group_rows, float* C, int ldc, int M, int N, int K,
                              bool relu_a, GemmEpi epi, const float* xmul, float* masked, cudaStream_t st);
 // hr_hi/hr_lo (optional): relu(h) as 16-bit hi/lo planes [B*T][2H] - the fc1 operand of the tensor-core head
+// gates_save/cseq (optional, training): gate activations i,f,g,o written over gates_x in place, cell states [B*T][2H]
 cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float* hout, float* hx,
                                  unsigned int* barrier, int B, int T, cudaStream_t st, elt16* hr_hi = nullptr,
-                                 elt16* hr_lo = nullptr, int elt = 0);
+                                 elt16* hr_lo = nullptr, int elt = 0, float* gates_save = nullptr, float* cseq = nullptr);
 size_t lstm_rec_scratch_bytes(const vs_engine* e, int B);
 // layout converters for the debug hooks
 cudaError_t launch_nchw_to_plane(const float* nchw, float* plane, int B, int C, int T, int F, cudaStream_t st);

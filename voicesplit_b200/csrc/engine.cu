@@ -218,6 +218,7 @@ int vs_engine_destroy(vs_engine* e) {
     if (!e) return VS_OK;
     pipe_destroy(e);
     free_params(e);
+    train_free(e);
     tc_destroy(e);
     if (e->prof) {
         for (cudaEvent_t ev : ((Prof*)e->prof)->ev) cudaEventDestroy(ev);
@@ -268,6 +269,8 @@ int vs_engine_load_params(vs_engine* e, const vs_params* p, void* stream) {
     VS_CUDA_TRY(cudaMemcpyAsync(e->fc2_b, p->fc2_b, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
     VS_CUDA_TRY(cudaGetLastError());
     int rc = tc_pack(e, st);
+    if (rc != VS_OK) return rc;
+    rc = train_pack(e, p, st);
     if (rc != VS_OK) return rc;
     e->loaded = true;
     return VS_OK;

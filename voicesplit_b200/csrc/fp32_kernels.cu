@@ -5,6 +5,7 @@
 // f in [F, Fp) are kept at zero by every producer, which is the reference's ZeroPad2d along F
 // (models/voicesplit/model.py:16-47) in the flattened pixel index.
 #include "common.cuh"
+#include "train.cuh"
 
 namespace vs {
 
@@ -44,6 +45,16 @@ __global__ void __launch_bounds__(256) k_front_fp32(const float* __restrict__ x,
     float4* dst = reinterpret_cast<float4*>(plane + (((size_t)b * T + t) * Fp + f) * 64 + cg * 8);
     dst[0] = make_float4(out[0], out[1], out[2], out[3]);
     dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
+cudaError_t launch_front_fp32_ex(const vs_engine* e, const float* x, float* plane, const float* w, const float* scale, const float* shift,
+                                 int act, int B, int T, cudaStream_t st) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    dim3 grid((Fp + 31) / 32, T, B);
+    if (act == VS_ACT_RELU) k_front_fp32<VS_ACT_RELU><<<grid, 256, 0, st>>>(x, plane, w, scale, shift, T, F, Fp);
+    else if (act == VS_ACT_NONE) k_front_fp32<VS_ACT_NONE><<<grid, 256, 0, st>>>(x, plane, w, scale, shift, T, F, Fp);
+    else k_front_fp32<VS_ACT_MISH><<<grid, 256, 0, st>>>(x, plane, w, scale, shift, T, F, Fp);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_front_fp32(const vs_engine* e, const float* x, float* plane, int B, int T, cudaStream_t st) {
@@ -125,6 +136,17 @@ __global__ void __launch_bounds__(256) k_conv_fp32(const float* __restrict__ in,
     }
 }
 
+cudaError_t launch_conv_fp32_ex(const vs_engine* e, int layer, const float* in, float* out, const float* w, const float* scale,
+                                const float* shift, int act, int B, int T, cudaStream_t st) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    const ConvGeom g = kConv[layer];
+    dim3 grid((Fp + 63) / 64, T, B);
+    if (act == VS_ACT_RELU) k_conv_fp32<VS_ACT_RELU><<<grid, 256, 0, st>>>(in, out, w, scale, shift, T, F, Fp, g.kh, g.kw, g.dil);
+    else if (act == VS_ACT_NONE) k_conv_fp32<VS_ACT_NONE><<<grid, 256, 0, st>>>(in, out, w, scale, shift, T, F, Fp, g.kh, g.kw, g.dil);
+    else k_conv_fp32<VS_ACT_MISH><<<grid, 256, 0, st>>>(in, out, w, scale, shift, T, F, Fp, g.kh, g.kw, g.dil);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conv_fp32(const vs_engine* e, int layer, const float* in, float* out, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
     const ConvGeom g = kConv[layer];
@@ -170,6 +192,17 @@ __global__ void __launch_bounds__(256) k_point8_fp32(const float* __restrict__ p
     float* dst = xcat + (size_t)bt * 8 * F + f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) dst[(size_t)c * F] = activate<ACT>(fmaf(acc[c], sc[c], sh[c]));
+}
+
+cudaError_t launch_point8_fp32_ex(const vs_engine* e, const float* plane, float* xcat, const float* w, const float* scale,
+                                  const float* shift, int act, int B, int T, cudaStream_t st) {
+    const int F = e->d.num_freq, Fp = padded_freq(F);
+    long long npix = (long long)B * T * F;
+    unsigned grid = (unsigned)((npix + 255) / 256);
+    if (act == VS_ACT_RELU) k_point8_fp32<VS_ACT_RELU><<<grid, 256, 0, st>>>(plane, xcat, w, scale, shift, T, F, Fp, npix);
+    else if (act == VS_ACT_NONE) k_point8_fp32<VS_ACT_NONE><<<grid, 256, 0, st>>>(plane, xcat, w, scale, shift, T, F, Fp, npix);
+    else k_point8_fp32<VS_ACT_MISH><<<grid, 256, 0, st>>>(plane, xcat, w, scale, shift, T, F, Fp, npix);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_point8_fp32(const vs_engine* e, const float* plane, float* xcat, int B, int T, cudaStream_t st) {
@@ -288,11 +321,12 @@ __device__ __forceinline__ void dir_barrier(unsigned int* counter, unsigned int 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 1) k_lstm_rec_fp32(const float* __restrict__ gates_x, const float* __restrict__ whh,
+__global__ void __launch_bounds__(256, 1) k_lstm_rec_fp32(const float* gates_x /* may alias gates_save */, const float* __restrict__ whh,
                                                           float* __restrict__ hout, float* hx, float* cstate,
                                                           unsigned int* barrier, unsigned int barrier_base,
                                                           int B, int Bp, int T, int H, int nslices,
-                                                          elt16* __restrict__ hr_hi, elt16* __restrict__ hr_lo, int elt) {
+                                                          elt16* __restrict__ hr_hi, elt16* __restrict__ hr_lo, int elt,
+                                                          float* gates_save, float* cseq) {
     extern __shared__ __align__(16) float smem[];
     float* wt = smem;                  // [H][kHS][4]   (k, unit, gate)
     float* ht = smem + (size_t)H * 32; // [H][kBT]
@@ -357,6 +391,11 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec_fp32(const float* __restric
                     float h_new = og * tanhf(c_new);
                     *cp = c_new;
                     hnext[(size_t)hj * Bp + b] = h_new;
+                    if (gates_save) {   // training: keep what the backward recurrence needs
+                        const size_t gi = ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H + hj;
+                        gates_save[gi] = ig; gates_save[gi + H] = fg; gates_save[gi + 2 * H] = gg; gates_save[gi + 3 * H] = og;
+                        cseq[((size_t)b * T + t) * 2 * H + (size_t)d * H + hj] = c_new;
+                    }
                     const size_t oidx = ((size_t)b * T + t) * 2 * H + (size_t)d * H + hj;
                     hout[oidx] = h_new;
                     if (hr_hi) {
@@ -381,7 +420,8 @@ size_t lstm_rec_scratch_bytes(const vs_engine* e, int B) {
 
 
 cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float* hout, float* hx,
-                                 unsigned int* barrier, int B, int T, cudaStream_t st, elt16* hr_hi, elt16* hr_lo, int elt) {
+                                 unsigned int* barrier, int B, int T, cudaStream_t st, elt16* hr_hi, elt16* hr_lo, int elt,
+                                 float* gates_save, float* cseq) {
     const int H = e->d.lstm_dim;
     const int nslices = (H + kHS - 1) / kHS;
     const int Bp = (int)align_up((size_t)B, kBT);
@@ -398,7 +438,7 @@ cudaError_t launch_lstm_rec_fp32(const vs_engine* e, const float* gates_x, float
     int Bv = B, Bpv = Bp, Tv = T, Hv = H, ns = nslices;
     void* args[] = {(void*)&gates_x, (void*)&whh, (void*)&hout, (void*)&hx, (void*)&cstate, (void*)&barrier,
                     (void*)&base, (void*)&Bv, (void*)&Bpv, (void*)&Tv, (void*)&Hv, (void*)&ns,
-                    (void*)&hr_hi, (void*)&hr_lo, (void*)&elt};
+                    (void*)&hr_hi, (void*)&hr_lo, (void*)&elt, (void*)&gates_save, (void*)&cseq};
     return cudaLaunchCooperativeKernel((const void*)k_lstm_rec_fp32, dim3(2 * nslices), dim3(256), args, smem, st);
 }
 

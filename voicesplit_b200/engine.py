@@ -144,6 +144,58 @@ class MaskEngine:
                                                ctypes.c_void_p(st)), "vs_conv_stack")
         return out
 
+    # ---- training (fp32, batch-statistics BatchNorm, full backward) ------------------------------
+    PARAM_ORDER = tuple([k for l in range(8) for k in (f"conv.{CONV_IDX[l]}.weight", f"conv.{CONV_IDX[l]}.bias",
+                                                        f"conv.{BN_IDX[l]}.weight", f"conv.{BN_IDX[l]}.bias")] +
+                        [f"lstm.{n}_l0{sfx}" for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")] +
+                        ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"])
+
+    def train_forward(self, x, emb, bn_buffers=None, momentum=0.1):
+        """Forward in BatchNorm-training mode.  bn_buffers: {state_dict key: tensor} of the running_mean /
+        running_var / num_batches_tracked buffers to update in place (or None).  Returns (mask, saved)."""
+        self._check_inputs(x, emb)
+        x = x.detach().to(torch.float32).contiguous()
+        emb = emb.detach().to(torch.float32).contiguous()
+        B, T, _ = x.shape
+        with torch.cuda.device(x.device):
+            need = int(self.lib.vs_train_workspace_bytes(self.handle, B, T))
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            mask = torch.empty_like(x)
+            state = None
+            if bn_buffers is not None:
+                state = _cabi.VsTrainState()
+                for l in range(8):
+                    state.running_mean[l] = bn_buffers[f"conv.{BN_IDX[l]}.running_mean"].data_ptr()
+                    state.running_var[l] = bn_buffers[f"conv.{BN_IDX[l]}.running_var"].data_ptr()
+                    state.num_batches_tracked[l] = bn_buffers[f"conv.{BN_IDX[l]}.num_batches_tracked"].data_ptr()
+                state.momentum = float(momentum)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_train_forward(self.handle, ctypes.byref(state) if state is not None else None, _ptr(x), _ptr(emb),
+                                                  _ptr(mask), B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_train_forward")
+        return mask, (ws, need, x, emb)
+
+    def train_backward(self, saved, mask, grad_mask, shapes):
+        """shapes: {state_dict key: shape} of the parameters.  Returns ({key: grad tensor}, grad_emb)."""
+        ws, need, x, emb = saved
+        B, T, _ = x.shape
+        grad_mask = grad_mask.detach().to(torch.float32).contiguous()
+        grads = {k: torch.empty(shapes[k], dtype=torch.float32, device=x.device) for k in self.PARAM_ORDER}
+        gemb = torch.empty_like(emb)
+        g = _cabi.VsGrads()
+        for l in range(8):
+            g.conv_w[l] = grads[f"conv.{CONV_IDX[l]}.weight"].data_ptr(); g.conv_b[l] = grads[f"conv.{CONV_IDX[l]}.bias"].data_ptr()
+            g.bn_gamma[l] = grads[f"conv.{BN_IDX[l]}.weight"].data_ptr(); g.bn_beta[l] = grads[f"conv.{BN_IDX[l]}.bias"].data_ptr()
+        for d, sfx in enumerate(("", "_reverse")):
+            g.w_ih[d] = grads[f"lstm.weight_ih_l0{sfx}"].data_ptr(); g.w_hh[d] = grads[f"lstm.weight_hh_l0{sfx}"].data_ptr()
+            g.b_ih[d] = grads[f"lstm.bias_ih_l0{sfx}"].data_ptr(); g.b_hh[d] = grads[f"lstm.bias_hh_l0{sfx}"].data_ptr()
+        g.fc1_w, g.fc1_b = grads["fc1.weight"].data_ptr(), grads["fc1.bias"].data_ptr()
+        g.fc2_w, g.fc2_b = grads["fc2.weight"].data_ptr(), grads["fc2.bias"].data_ptr()
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_train_backward(self.handle, _ptr(x), _ptr(emb), _ptr(mask), _ptr(grad_mask), ctypes.byref(g), _ptr(gemb),
+                                                   B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_train_backward")
+        return grads, gemb
+
     # ---- test hooks ---------------------------------------------------------------------------
     def debug_conv_layer(self, layer, inp, precision="fp32"):
         inp = inp.detach().to(torch.float32).contiguous()

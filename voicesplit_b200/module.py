@@ -52,6 +52,26 @@ def _conv_stack_modules(activation):
     return mods
 
 
+class _MaskTrainFn(torch.autograd.Function):
+    """Training-mode forward/backward through the engine (fp32 kernels, batch-statistics BatchNorm)."""
+
+    @staticmethod
+    def forward(ctx, module, x, emb, *params):
+        eng = module._sync_engine(x.device)
+        buffers = {k: v for k, v in module.named_buffers()}
+        mask, saved = eng.train_forward(x, emb, buffers, momentum=0.1)
+        ctx.eng, ctx.saved = eng, saved
+        ctx.shapes = {k: tuple(p.shape) for k, p in module.named_parameters()}
+        ctx.save_for_backward(mask)
+        return mask
+
+    @staticmethod
+    def backward(ctx, grad_mask):
+        (mask,) = ctx.saved_tensors
+        grads, gemb = ctx.eng.train_backward(ctx.saved, mask, grad_mask, ctx.shapes)
+        return (None, None, gemb) + tuple(grads[k] for k in ctx.eng.PARAM_ORDER)
+
+
 class MaskEstimator(nn.Module):
     ACTIVATION = "mish"
 
@@ -96,15 +116,19 @@ class MaskEstimator(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("voicesplit_b200 runs on sm_100a CUDA devices only: move the module and inputs "
                                "with .cuda() (there is no CPU or PyTorch fallback)")
-        if self.training:
-            raise NotImplementedError(
-                "training-mode forward (batch-statistics BatchNorm) and the backward kernels are not built yet; "
-                "call .eval() - see DESIGN.md 'out of scope this round'")
 
     # ---- the reference contract ---------------------------------------------------------------
     def forward(self, x, speaker_embedding):
         """x: [B, T, num_freq], speaker_embedding: [B, emb_dim] -> mask [B, T, num_freq]."""
         self._guard(x)
+        if self.training:
+            # train.py:84,94: BatchNorm uses batch statistics and updates its running buffers; the output
+            # carries a grad_fn whose backward fills .grad of every parameter (fp32 kernels)
+            if x.requires_grad:
+                raise NotImplementedError("the gradient w.r.t. the input spectrogram is not provided")
+            names = dict(self.named_parameters())
+            params = [names[k] for k in MaskEngine.PARAM_ORDER]
+            return _MaskTrainFn.apply(self, x, speaker_embedding.to(x.device), *params)
         eng = self._sync_engine(x.device)
         return eng.forward(x, speaker_embedding.to(x.device), precision=self.precision)
 
