@@ -52,13 +52,21 @@ def test_train_forward_backward_match_autograd(model_name, dims, B, T):
             assert torch.allclose(msd[k].cpu(), ref_sd[k], atol=2e-5, rtol=1e-4), k
         if "num_batches" in k:
             assert int(msd[k]) == 1
+    # relative to each gradient's own scale; a conv bias in front of a BatchNorm has an analytically ZERO
+    # gradient (the batch mean removes it), so both sides hold rounding noise there: absolute floor
+    gmax = max(float(ref_sd[k].grad.abs().max()) for k, _ in m.named_parameters())
     worst = {}
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         r = ref_sd[k].grad
-        scale = max(1e-6, float(r.abs().max()))
-        worst[k] = float((p.grad.cpu() - r).abs().max()) / scale
-    bad = {k: v for k, v in worst.items() if v > 2e-3}
+        err = float((p.grad.cpu() - r).abs().max())
+        worst[k] = (err, float(r.abs().max()))
+    conv_bias = {f"conv.{i}.bias": f"conv.{i}.weight" for i in (1, 5, 9, 13, 17, 21, 25, 28)}
+
+    def scale(k):   # analytically-zero conv-bias gradients are judged on the scale of their layer's weight gradient
+        return max(worst[k][1], worst[conv_bias[k]][1]) if k in conv_bias else worst[k][1]
+    bad = {k: v for k, v in worst.items() if v[0] > 2e-3 * scale(k) + 1e-6 * gmax}
+    print({k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in worst.items()})
     assert not bad, bad
     assert (et.grad.cpu() - ref_gemb).abs().max() < 2e-3 * max(1e-6, float(ref_gemb.abs().max()))
 
