@@ -46,3 +46,47 @@ def test_two_rank_gloo_aggregation():
         assert p.exitcode == 0
     assert ms == pytest.approx(150.0)                  # max over ranks, not the mean
     assert thr == pytest.approx(257 / 0.150)           # all utterances / slowest rank
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    d = vdist.init("gloo")
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))          # rank-dependent gradients
+    n = vdist.allreduce_gradients(params, d)
+    if rank == 0:
+        out.put((n, [p.grad.clone() for p in params]))
+    d.barrier()
+    d.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_averages_over_ranks():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n, grads = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n == 22
+    assert torch.allclose(grads[0], torch.full((5, 3), 1.5)) and torch.allclose(grads[1], torch.full((7,), 3.0))
+
+
+def test_si_snr_matches_reference_formula():
+    """voicesplit_b200/losses.py against the reference criterion when the reference tree is present."""
+    from oracle import ref_import
+    from voicesplit_b200.losses import si_snr_with_pit
+    torch.manual_seed(1)
+    est, src = torch.randn(3, 1, 500), torch.randn(3, 1, 500)
+    lengths = torch.tensor([500, 321, 77])
+    mine = si_snr_with_pit(est.clone(), src.clone(), lengths)
+    assert torch.isfinite(mine)
+    if ref_import.available():
+        _, _, gu = ref_import.load()
+        ref = gu.SiSNR_With_Pit()(est.clone(), src.clone(), lengths)
+        assert torch.allclose(mine, ref, atol=1e-5)

@@ -1,0 +1,96 @@
+"""Training-step benchmark (BASELINE config 4 shape): forward (batch-stat BatchNorm) + Si-SNR-PIT loss +
+backward + ONE flat NCCL gradient all-reduce + Adam step, data-parallel over the ranks it is launched on.
+
+    python tools/train_bench.py --batch 8 --steps 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_bench.py --batch 8
+
+Prints one JSON line (rank 0).  Not the headline metric (bench.py is); numbers go to DESIGN.md section 7.
+BatchNorm statistics are per rank (what "a single NCCL all-reduce" implies)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from voicesplit_b200 import config, dist as vdist, synth  # noqa: E402
+from voicesplit_b200.losses import si_snr_with_pit  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=301)
+    ap.add_argument("--freq", type=int, default=601)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--cpu-reference", action="store_true", help="also time PyTorch autograd on the host CPU (B=2)")
+    args = ap.parse_args()
+    rank, world, local = vdist.env_rank()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = vdist.init("nccl", dev)
+    from models.voicesplit.model import VoiceSplit
+    dims = synth.make_dims(args.freq, 256, 400, 600)
+    model = VoiceSplit(config.AttrDict(synth.make_config_dict(dims)))
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()})
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    B, T, F = args.batch, args.frames, args.freq
+    x, emb = synth.make_inputs(B, T, dims, 100 + rank)
+    x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
+    target = torch.rand(B, T, F, device=dev) * x
+    lengths = torch.full((B,), T * F, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        mask = model(x, emb)
+        loss = si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths)
+        loss.backward()
+        n = vdist.allreduce_gradients(model.parameters(), dist)
+        opt.step()
+        return loss, n
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = []
+    for _ in range(args.steps):
+        loss, nred = step()
+        losses.append(float(loss.detach()))
+    e1.record()
+    torch.cuda.synchronize()
+    thr, ms = vdist.aggregate_throughput(B * args.steps, e0.elapsed_time(e1), dist, dev)
+    if rank == 0:
+        out = {"metric": "training utterances/s (forward + Si-SNR-PIT + backward + grad all-reduce + Adam)", "value": thr,
+               "n_gpus": world, "per_gpu_batch": B, "frames": T, "freq_bins": F, "ms_per_step": ms / args.steps,
+               "allreduce_floats": nred, "losses": losses, "arithmetic": "fp32 CUDA cores (training path)",
+               "bn_statistics": "per rank"}
+        if args.cpu_reference:
+            from oracle import torch_port
+            sd = {k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()}
+            for k, v in sd.items():
+                if v.dtype == torch.float32 and "running" not in k:
+                    v.requires_grad_(True)
+            xc, ec = synth.make_inputs(2, T, dims, 100)
+            xc, ec = torch.from_numpy(xc), torch.from_numpy(ec)
+            t0 = time.perf_counter()
+            m = torch_port.forward_train(sd, xc, ec)
+            si_snr_with_pit((m * xc).view(2, 1, -1), (xc * 0.5).view(2, 1, -1), torch.full((2,), T * F)).backward()
+            dt = time.perf_counter() - t0
+            out["cpu_reference"] = {"value": 2 / dt, "unit": "utterances/s", "sample": f"B=2 forward+backward via torch autograd (oracle/torch_port.forward_train), {torch.get_num_threads()} threads, {dt:.1f} s"}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,3 +55,22 @@ def aggregate_throughput(local_units, local_ms, dist, device="cpu"):
     total = sum_over_ranks(local_units, dist, device)
     ms = max_over_ranks(local_ms, dist, device)
     return total / (ms / 1e3), ms
+
+
+def allreduce_gradients(parameters, dist, world=None):
+    """Data-parallel step of BASELINE config 4: ONE all-reduce over a flat fp32 buffer holding every
+    parameter gradient (18.9 M floats = 75.5 MB at the shipped config), then divide by the world size
+    (the loss is a batch mean) and scatter back into the .grad tensors.  No-op for a single process."""
+    params = [p for p in parameters if p.grad is not None]
+    if dist is None or not params:
+        return 0
+    world = world or dist.get_world_size()
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel()
