@@ -12,8 +12,9 @@ from this repo unchanged:
 * `forward(x[B,T,F], speaker_embedding[B,E]) -> mask[B,T,F]` (model.py:66-89).
 
 The layers below only *hold* parameters - none of them is ever called.  The arithmetic runs in
-hand-written sm_100a kernels behind the C ABI (include/voicesplit_b200.h).  There is no CPU path
-and no PyTorch fallback: forward raises if the inputs are not on a CUDA device.
+hand-written sm_100a kernels behind the C ABI (include/voicesplit_b200.h), in eval mode (tensor-core
+precision modes) and in train mode (fp32 kernels, autograd through vs_train_forward/backward).  There
+is no CPU path and no PyTorch fallback: forward raises if the inputs are not on a CUDA device.
 """
 from __future__ import annotations
 
