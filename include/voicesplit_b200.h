@@ -162,6 +162,9 @@ typedef struct vs_grads {
     float* fc2_w;
     float* fc2_b;
 } vs_grads;
+/* The conv forward and data-gradient of the training path run on the tcgen05 conv kernel by default
+ * (fp16x3 activations, bf16x3 gradients: fp32-grade, no loss scaling); 0 selects the fp32 CUDA-core convs. */
+int vs_engine_set_train_tensor_cores(vs_engine* e, int32_t enabled);
 size_t vs_train_workspace_bytes(const vs_engine* e, int32_t B, int32_t T);
 int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, const float* emb, float* mask,
                      int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream);

@@ -24,10 +24,11 @@ def _cpu_reference(sd_np, x, emb, gw, activation):
     return mask.detach(), sd, et.grad
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("model_name,dims,B,T", [("voicesplit", synth.make_dims(33, 16, 24, 40), 3, 21),
                                                  ("voicefilter", synth.make_dims(17, 8, 16, 24), 2, 9),
                                                  ("voicesplit", synth.make_dims(41, 20, 28, 36), 2, 40)])
-def test_train_forward_backward_match_autograd(model_name, dims, B, T):
+def test_train_forward_backward_match_autograd(model_name, dims, B, T, tensor_cores):
     from models.voicefilter.model import VoiceFilter
     from models.voicesplit.model import VoiceSplit
     sd_np = synth.make_state_dict(dims, 5, "stress")
@@ -39,6 +40,7 @@ def test_train_forward_backward_match_autograd(model_name, dims, B, T):
     m = cls(config.AttrDict(synth.make_config_dict(dims, model_name)))
     m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
     m = m.cuda().train()
+    m.train_tensor_cores = tensor_cores
     et = torch.from_numpy(emb).cuda().requires_grad_(True)
     mask = m(torch.from_numpy(x).cuda(), et)
     assert mask.requires_grad

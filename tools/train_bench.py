@@ -57,6 +57,19 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    # per-kernel breakdown of one step (forward and backward are separate engine calls)
+    eng = model._engine
+    eng.set_profiling(True)
+    opt.zero_grad(set_to_none=True)
+    mask = model(x, emb)
+    fwd = eng.profile_read()
+    si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths).backward()
+    bwd = eng.profile_read()
+    eng.set_profiling(False)
+    breakdown = {}
+    for tag, rows in (("fwd", fwd), ("bwd", bwd)):
+        for name, ms in rows:
+            breakdown[f"{tag}:{name}"] = round(breakdown.get(f"{tag}:{name}", 0.0) + ms, 3)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -73,7 +86,7 @@ def main():
         out = {"metric": "training utterances/s (forward + Si-SNR-PIT + backward + grad all-reduce + Adam)", "value": thr,
                "n_gpus": world, "per_gpu_batch": B, "frames": T, "freq_bins": F, "ms_per_step": ms / args.steps,
                "allreduce_floats": nred, "losses": losses, "arithmetic": "fp32 CUDA cores (training path)",
-               "bn_statistics": "per rank"}
+               "bn_statistics": "per rank", "kernel_ms": breakdown}
         if args.cpu_reference:
             from oracle import torch_port
             sd = {k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()}

@@ -109,6 +109,7 @@ struct vs_engine {
     float* bn_gamma[8] = {};
     float* bn_beta[8] = {};
     float* ones64 = nullptr, *zeros64 = nullptr;
+    bool train_tc = true;       // training: forward and data-gradient convs on the tcgen05 conv kernel (else fp32 CUDA cores)
 
     // host staging for vs_forward_host (grow-only)
     void* stage = nullptr;
@@ -129,7 +130,10 @@ namespace vs {
 // kernel ids reported by vs_profile_read
 enum KernelId {
     KID_FRONT = 0, KID_CONV1 = 1 /* +layer-1 for layers 1..6 */, KID_POINT8 = 7, KID_EMB_BIAS = 8, KID_INPROJ = 9,
-    KID_LSTM_REC = 10, KID_FC1 = 11, KID_FC2 = 12, KID_CONVERT = 13, KID_HEAD = 14
+    KID_LSTM_REC = 10, KID_FC1 = 11, KID_FC2 = 12, KID_CONVERT = 13, KID_HEAD = 14,
+    // training path
+    KID_TR_CONV_FWD = 20, KID_TR_BN_STATS = 21, KID_TR_BN_ACT = 22, KID_TR_BN_BWD = 23, KID_TR_WGRAD = 24, KID_TR_DGRAD = 25,
+    KID_TR_GEMM = 26, KID_TR_LSTM_BWD = 27, KID_TR_MISC = 28
 };
 void prof_begin(vs_engine* e, cudaStream_t st);
 void prof_after(vs_engine* e, int id, cudaStream_t st);

@@ -268,9 +268,9 @@ int vs_engine_load_params(vs_engine* e, const vs_params* p, void* stream) {
     VS_CUDA_TRY(cudaMemcpyAsync(e->fc2_w, p->fc2_w, sizeof(float) * F * N1, cudaMemcpyDeviceToDevice, st));
     VS_CUDA_TRY(cudaMemcpyAsync(e->fc2_b, p->fc2_b, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
     VS_CUDA_TRY(cudaGetLastError());
-    int rc = tc_pack(e, st);
+    int rc = train_pack(e, p, st);      // first: tc_pack also tiles the data-gradient weights it produces
     if (rc != VS_OK) return rc;
-    rc = train_pack(e, p, st);
+    rc = tc_pack(e, st);
     if (rc != VS_OK) return rc;
     e->loaded = true;
     return VS_OK;

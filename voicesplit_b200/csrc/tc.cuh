@@ -38,6 +38,10 @@ size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision);
 int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32,
                  const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, void* gemm_ws,
                  const TcLstmBuffers& lb, cudaStream_t st);
+// training (train.cu): raw forward conv / data-gradient conv of layer 1..6 on k_conv_tc, 3 passes, fp32 output plane
+int tc_train_conv(vs_engine* e, int layer, bool dgrad, const elt16* in_hi, const elt16* in_lo, const float* shift, float* out32, int B, int T,
+                  int elt, int kid, cudaStream_t st);
+
 // ---- tc_lstm.cu: tensor-core recurrent kernel ---------------------------------------------------
 int tc_lstm_pack(vs_engine* e, void** slot, cudaStream_t st);
 void tc_lstm_destroy(void* slot);

@@ -47,15 +47,17 @@ struct ConvTcArgs {
     const float* shift;
     elt16* out_hi;
     elt16* out_lo;  // may be null (single-pass modes)
+    float* out32;   // OUT32 kernels (training): fp32 plane [B][Q][64] instead of the 16-bit planes
 };
 
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
+    if (ACT == 2) return x;   // pass-through: raw conv output (training forward before BatchNorm, data gradients)
     if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
     return mish_f(x);
 }
 
-template <int ACT, int ELT>
+template <int ACT, int ELT, bool OUT32>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
                                                     const __grid_constant__ CUtensorMap tm_w_hi,
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
         const int cgrp = (warp - 2) >> 2;                // which 32-column chunks this warp takes
         const int co = quad * 16 + (lane >> 1), h = lane & 1;
         const float sc = a.scale[co], sh = a.shift[co];
-        const bool want_lo = a.out_lo != nullptr;
+        const bool want_lo = !OUT32 && a.out_lo != nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, aph = (it >> 1) & 1;
@@ -193,8 +195,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
             int f = (q0 + h + cgrp * 32) % a.Fp;         // frequency index of this lane's first pixel
-            elt16* ohi = a.out_hi + ((size_t)b * a.Q + q0) * 64 + co;
-            elt16* olo = want_lo ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
+            elt16* ohi = OUT32 ? nullptr : a.out_hi + ((size_t)b * a.Q + q0) * 64 + co;
+            elt16* olo = (!OUT32 && want_lo) ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
+            float* o32 = OUT32 ? a.out32 + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
             for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (kEpiWarps / 4)) {
                 uint32_t r[32];
                 uint32_t nxt = 0;
@@ -212,10 +215,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                     const int p = c0 + 2 * m + h;
                     if (p < useful && q0 + p < a.Q) {
                         float y = (f < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
-                        elt16 yh, yl;
-                        split16<ELT>(y, yh, yl);
-                        ohi[(size_t)p * 64] = yh;
-                        if (want_lo) olo[(size_t)p * 64] = yl;
+                        if (OUT32) {
+                            o32[(size_t)p * 64] = y;
+                        } else {
+                            elt16 yh, yl;
+                            split16<ELT>(y, yh, yl);
+                            ohi[(size_t)p * 64] = yh;
+                            if (want_lo) olo[(size_t)p * 64] = yl;
+                        }
                     }
                     f += 2;
                     if (f >= a.Fp) f -= a.Fp;
@@ -415,6 +422,9 @@ struct TcState {
     elt16* w_hi[2][8] = {};   // [elt][layer]
     elt16* w_lo[2][8] = {};
     float* scale_tc[8] = {};  // BN scale divided by the layer's power-of-two weight scale
+    elt16* wT_hi[2][8] = {};  // training: data-gradient weights (taps flipped, channels transposed), same tile format
+    elt16* wT_lo[2][8] = {};
+    float* unscale[8] = {};   // 64 copies of 1 / (power-of-two weight scale): epilogue scale of the raw-output convs
     unsigned int* wmax = nullptr;
     int max_smem = 0;
 };
@@ -433,8 +443,8 @@ void tc_destroy(vs_engine* e) {
     tc_gemm_destroy(e);
     tc_lstm_destroy(s->lstm);
     for (int l = 0; l < 8; ++l) {
-        for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); }
-        cudaFree(s->scale_tc[l]);
+        for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); cudaFree(s->wT_hi[t][l]); cudaFree(s->wT_lo[t][l]); }
+        cudaFree(s->scale_tc[l]); cudaFree(s->unscale[l]);
     }
     cudaFree(s->wmax);
     delete s;
@@ -453,14 +463,21 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
             for (int t = 0; t < 2; ++t) {
                 VS_CUDA_TRY(cudaMalloc(&s->w_hi[t][l], n * sizeof(elt16)));
                 VS_CUDA_TRY(cudaMalloc(&s->w_lo[t][l], n * sizeof(elt16)));
+                VS_CUDA_TRY(cudaMalloc(&s->wT_hi[t][l], n * sizeof(elt16)));
+                VS_CUDA_TRY(cudaMalloc(&s->wT_lo[t][l], n * sizeof(elt16)));
             }
             VS_CUDA_TRY(cudaMalloc(&s->scale_tc[l], 64 * sizeof(float)));
+            VS_CUDA_TRY(cudaMalloc(&s->unscale[l], 64 * sizeof(float)));
         }
         const int nw = g.cout * g.cin * g.kh * g.kw;
         k_absmax<<<(nw + 255) / 256, 256, 0, st>>>(e->conv_w32[l], nw, s->wmax + l);
         k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_hi[0][l], s->w_lo[0][l],
                                                                     s->w_hi[1][l], s->w_lo[1][l], g.kh, g.kw, n_j);
         k_scale_tc<<<1, 64, 0, st>>>(e->conv_scale[l], s->wmax + l, s->scale_tc[l], 64);
+        // training: the same power-of-two scale serves the flipped/transposed data-gradient weights (same values)
+        k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_wT32[l], s->wmax + l, s->wT_hi[0][l], s->wT_lo[0][l],
+                                                                    s->wT_hi[1][l], s->wT_lo[1][l], g.kh, g.kw, n_j);
+        k_scale_tc<<<1, 64, 0, st>>>(e->ones64, s->wmax + l, s->unscale[l], 64);
     }
     VS_CUDA_TRY(cudaGetLastError());
     int rc = tc_lstm_pack(e, &s->lstm, st);
@@ -469,8 +486,36 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
 }
 void* tc_lstm_slot(vs_engine* e) { return ((TcState*)e->tc)->lstm; }
 
+struct ConvTcCall {            // what differs between the eval layers and the training uses of the kernel
+    const elt16 *w_hi, *w_lo;
+    const float *scale, *shift;
+    int act;                   // VS_ACT_* or 2 (pass-through)
+    float* out32;              // non-null: fp32 output plane
+    int kid;
+};
+static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo, elt16* out_hi, elt16* out_lo, int B, int T,
+                             int passes, int elt, const ConvTcCall& call, cudaStream_t st);
+
 static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo,
                           elt16* out_hi, elt16* out_lo, int B, int T, int precision, cudaStream_t st) {
+    TcState* s = (TcState*)e->tc;
+    const int elt = tc_elt(precision);
+    ConvTcCall call{s->w_hi[elt][layer], s->w_lo[elt][layer], s->scale_tc[layer], e->conv_shift[layer], e->d.activation, nullptr,
+                    KID_CONV1 + layer - 1};
+    return launch_conv_tc_ex(e, layer, in_hi, in_lo, out_hi, out_lo, B, T, tc_passes(precision), elt, call, st);
+}
+
+// training: raw (pre-BatchNorm) forward conv, or the data gradient (flipped / transposed weights), fp32 output
+int tc_train_conv(vs_engine* e, int layer, bool dgrad, const elt16* in_hi, const elt16* in_lo, const float* shift, float* out32, int B, int T,
+                  int elt, int kid, cudaStream_t st) {
+    TcState* s = (TcState*)e->tc;
+    ConvTcCall call{dgrad ? s->wT_hi[elt][layer] : s->w_hi[elt][layer], dgrad ? s->wT_lo[elt][layer] : s->w_lo[elt][layer], s->unscale[layer],
+                    shift, 2, out32, kid};
+    return launch_conv_tc_ex(e, layer, in_hi, in_lo, nullptr, nullptr, B, T, 3, elt, call, st);
+}
+
+static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo, elt16* out_hi, elt16* out_lo, int B, int T,
+                             int passes, int elt, const ConvTcCall& call, cudaStream_t st) {
     TcState* s = (TcState*)e->tc;
     const ConvGeom g = kConv[layer];
     const int F = e->d.num_freq, Fp = padded_freq(F);
@@ -481,8 +526,7 @@ static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt
     a.total_tiles = B * a.tiles_per_utt;
     a.n_dt = g.kh; a.n_j = (g.kw + 1) / 2; a.halo = g.kw / 2;
     a.dt_stride = g.dil * Fp;
-    a.passes = tc_passes(precision);
-    const int elt = tc_elt(precision);
+    a.passes = passes;
     a.strip_rows = a.N + 8;
     a.box_rows = a.strip_rows;
     a.n_boxes = 1;
@@ -492,9 +536,9 @@ static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt
         a.box_rows = a.strip_rows / a.n_boxes;
         if (a.n_boxes > 64) { set_error("cannot split strip into TMA boxes"); return VS_ERR_INVALID; }
     }
-    a.act = e->d.activation;
-    a.scale = s->scale_tc[layer]; a.shift = e->conv_shift[layer];
-    a.out_hi = out_hi; a.out_lo = (a.passes == 3) ? out_lo : nullptr;
+    a.act = call.act;
+    a.scale = call.scale; a.shift = call.shift;
+    a.out_hi = out_hi; a.out_lo = (a.passes == 3) ? out_lo : nullptr; a.out32 = call.out32;
     const int strip_bytes = a.strip_rows * 128;
     const int fixed = 1024 + kWStages * kWTileBytes + 512;
     a.s_stages = (s->max_smem - fixed) / strip_bytes;
@@ -512,24 +556,27 @@ static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt
         uint64_t wd[2] = {64, (uint64_t)a.n_dt * a.n_j * 128};
         uint64_t ws[1] = {128};
         uint32_t wb[2] = {64, 128};
-        ok = ok && make_tmap_bf16(&tm_w_hi, s->w_hi[elt][layer], 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
-        ok = ok && make_tmap_bf16(&tm_w_lo, s->w_lo[elt][layer], 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_hi, (void*)call.w_hi, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_lo, (void*)call.w_lo, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
         if (!ok) { set_error("cuTensorMapEncodeTiled failed"); return VS_ERR_CUDA; }
     }
     int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
     cudaError_t ce;
-#define VS_CONV_TC(A, E)                                                                                  \
+#define VS_CONV_TC(A, E, O)                                                                               \
     do {                                                                                                  \
-        ce = cudaFuncSetAttribute(k_conv_tc<A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
-        if (ce == cudaSuccess) k_conv_tc<A, E><<<grid, kConvThreads, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+        if (ce == cudaSuccess) k_conv_tc<A, E, O><<<grid, kConvThreads, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
-    if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1); else VS_CONV_TC(VS_ACT_RELU, 0); }
-    else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1); else VS_CONV_TC(VS_ACT_MISH, 0); }
+    if (call.out32) {
+        if (call.act != 2) { set_error("fp32-output conv is pass-through only"); return VS_ERR_INVALID; }
+        if (elt) VS_CONV_TC(2, 1, true); else VS_CONV_TC(2, 0, true);
+    } else if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1, false); else VS_CONV_TC(VS_ACT_RELU, 0, false); }
+    else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1, false); else VS_CONV_TC(VS_ACT_MISH, 0, false); }
 #undef VS_CONV_TC
     if (ce == cudaSuccess) ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_error(std::string("k_conv_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
     e->launches++;
-    if (e->profiling) prof_after(e, KID_CONV1 + layer - 1, st);
+    if (e->profiling) prof_after(e, call.kid, st);
     return VS_OK;
 }
 

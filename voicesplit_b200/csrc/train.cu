@@ -4,6 +4,7 @@
 // layers reuses the forward conv kernel with flipped / transposed weights.
 // Reference: autograd through models/voicesplit/model.py:66-89 as driven by train.py:94-111.
 #include "train.cuh"
+#include "tc.cuh"
 
 namespace vs {
 
@@ -47,6 +48,8 @@ __global__ void k_fill(float* p, float v, int n) {
 struct TrainWs {
     float* z[7];            // pre-BatchNorm conv outputs, planes [B][T][Fp][64]
     float *P, *G1, *G2;     // activation / gradient scratch planes
+    elt16 *Ahi, *Alo;       // a_l as fp16 hi/lo planes (operand of the tensor-core forward conv)
+    elt16 *Dhi, *Dlo;       // dz_l as bf16 hi/lo planes (operand of the tensor-core data-gradient conv)
     float *z7, *xcat, *dxcat;           // [M][8F]
     float *gates, *bias_u, *hout, *cseq, *hprev, *dh;   // LSTM
     float *y1, *dy1, *dz2;              // head
@@ -68,6 +71,8 @@ static TrainWs train_carve(const vs_engine* e, int B, int T, void* base) {
     TrainWs w{};
     for (int l = 0; l < 7; ++l) w.z[l] = (float*)take(plane);
     w.P = (float*)take(plane); w.G1 = (float*)take(plane); w.G2 = (float*)take(plane);
+    w.Ahi = (elt16*)take(plane / 2); w.Alo = (elt16*)take(plane / 2);
+    w.Dhi = (elt16*)take(plane / 2); w.Dlo = (elt16*)take(plane / 2);
     w.z7 = (float*)take(M * 8 * F * 4); w.xcat = (float*)take(M * 8 * F * 4); w.dxcat = (float*)take(M * 8 * F * 4);
     w.gates = (float*)take(M * 8 * H * 4); w.bias_u = (float*)take((size_t)B * 8 * H * 4);
     w.hout = (float*)take(M * 2 * H * 4); w.cseq = (float*)take(M * 2 * H * 4); w.hprev = (float*)take(M * 2 * H * 4); w.dh = (float*)take(M * 2 * H * 4);
@@ -82,13 +87,20 @@ static TrainWs train_carve(const vs_engine* e, int B, int T, void* base) {
     return w;
 }
 
-#define TR(e, st, call) VS_LAUNCH(e, KID_CONVERT, st, call)
+#define TR(e, st, call) VS_LAUNCH(e, KID_TR_MISC, st, call)
+#define TRK(e, id, st, call) VS_LAUNCH(e, id, st, call)
 
 }  // namespace vs
 
 using namespace vs;
 
 extern "C" {
+
+int vs_engine_set_train_tensor_cores(vs_engine* e, int32_t enabled) {
+    if (!e) { set_error("null engine"); return VS_ERR_INVALID; }
+    e->train_tc = enabled != 0;
+    return VS_OK;
+}
 
 size_t vs_train_workspace_bytes(const vs_engine* e, int32_t B, int32_t T) {
     if (!e || B < 1 || T < 1) return 0;
@@ -109,12 +121,19 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
     prof_begin(e, st);
     // conv stack with batch statistics: z_l = conv(a_{l-1}) + bias, a_l = act(BN_batch(z_l))
     for (int l = 0; l < 7; ++l) {
-        if (l == 0) TR(e, st, launch_front_fp32_ex(e, x, w.z[0], e->conv_w32[0], e->ones64, e->conv_bias[0], VS_ACT_NONE, B, T, st));
-        else TR(e, st, launch_conv_fp32_ex(e, l, w.P, w.z[l], e->conv_w32[l], e->ones64, e->conv_bias[l], VS_ACT_NONE, B, T, st));
-        TR(e, st, tr_bn_stats_plane(w.z[l], w.sums, F, Fp, M, e->num_sms, st));
+        if (l == 0) {
+            TRK(e, KID_TR_CONV_FWD, st, launch_front_fp32_ex(e, x, w.z[0], e->conv_w32[0], e->ones64, e->conv_bias[0], VS_ACT_NONE, B, T, st));
+        } else if (e->train_tc) {
+            int rc = tc_train_conv(e, l, false, w.Ahi, w.Alo, e->conv_bias[l], w.z[l], B, T, 1, KID_TR_CONV_FWD, st);
+            if (rc != VS_OK) return rc;
+        } else {
+            TRK(e, KID_TR_CONV_FWD, st, launch_conv_fp32_ex(e, l, w.P, w.z[l], e->conv_w32[l], e->ones64, e->conv_bias[l], VS_ACT_NONE, B, T, st));
+        }
+        TRK(e, KID_TR_BN_STATS, st, tr_bn_stats_plane(w.z[l], w.sums, F, Fp, M, e->num_sms, st));
         TR(e, st, tr_bn_finalize(w.sums, (double)M * F, e->bn_gamma[l], e->bn_beta[l], w.stat + l * 256, bn ? bn->running_mean[l] : nullptr,
                                  bn ? bn->running_var[l] : nullptr, bn ? (long long*)bn->num_batches_tracked[l] : nullptr, mom, 64, st));
-        TR(e, st, tr_bn_act_plane(act, w.z[l], w.P, w.stat + l * 256, F, Fp, M * Fp, st));
+        const bool tc_next = e->train_tc && l < 6;     // the next layer's conv reads the 16-bit planes
+        TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l], w.P, w.stat + l * 256, F, Fp, M * Fp, st, tc_next ? w.Ahi : nullptr, tc_next ? w.Alo : nullptr, 1));
     }
     TR(e, st, launch_point8_fp32_ex(e, w.P, w.z7, e->conv_w32[7], e->ones64, e->conv_bias[7], VS_ACT_NONE, B, T, st));
     TR(e, st, tr_bn_stats_cols(w.z7, w.sums, 8, F, M, e->num_sms, st));
@@ -144,21 +163,21 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
     prof_begin(e, st);
     // ---- head: mask = sigmoid(z2), z2 = y1 W2^T + b2, y1 = relu(rh W1^T + b1), rh = relu(h)
     TR(e, st, tr_sigmoid_bwd(grad_mask, mask, w.dz2, M * F, st));
-    TR(e, st, tr_gemm(w.dz2, 1, F, w.y1, N1, 1, g->fc2_w, N1, F, N1, Mi, false, st));               // dW2 [F][N1] = dz2^T y1
+    TRK(e, KID_TR_GEMM, st, tr_gemm(w.dz2, 1, F, w.y1, N1, 1, g->fc2_w, N1, F, N1, Mi, false, st));               // dW2 [F][N1] = dz2^T y1
     TR(e, st, tr_colsum(w.dz2, F, Mi, F, g->fc2_b, st));
-    TR(e, st, tr_gemm(w.dz2, F, 1, e->fc2_w, N1, 1, w.dy1, N1, Mi, N1, F, false, st));              // dy1 = dz2 W2
+    TRK(e, KID_TR_GEMM, st, tr_gemm(w.dz2, F, 1, e->fc2_w, N1, 1, w.dy1, N1, Mi, N1, F, false, st));              // dy1 = dz2 W2
     TR(e, st, tr_relu_mask(w.dy1, w.y1, M * N1, st));
     {
         long long n = M * 2 * H;
         k_relu_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.hout, w.hprev, n);                 // rh in hprev (reused below)
         TR(e, st, cudaGetLastError());
     }
-    TR(e, st, tr_gemm(w.dy1, 1, N1, w.hprev, 2 * H, 1, g->fc1_w, 2 * H, N1, 2 * H, Mi, false, st)); // dW1 [N1][2H] = dy1^T rh
+    TRK(e, KID_TR_GEMM, st, tr_gemm(w.dy1, 1, N1, w.hprev, 2 * H, 1, g->fc1_w, 2 * H, N1, 2 * H, Mi, false, st)); // dW1 [N1][2H] = dy1^T rh
     TR(e, st, tr_colsum(w.dy1, N1, Mi, N1, g->fc1_b, st));
-    TR(e, st, tr_gemm(w.dy1, N1, 1, e->fc1_w, 2 * H, 1, w.dh, 2 * H, Mi, 2 * H, N1, false, st));    // d rh = dy1 W1
+    TRK(e, KID_TR_GEMM, st, tr_gemm(w.dy1, N1, 1, e->fc1_w, 2 * H, 1, w.dh, 2 * H, Mi, 2 * H, N1, false, st));    // d rh = dy1 W1
     TR(e, st, tr_relu_mask(w.dh, w.hout, M * 2 * H, st));                                            // -> d lstm_out
     // ---- BiLSTM: recurrence backward turns the saved gate activations into pre-activation gradients (in place)
-    VS_LAUNCH(e, KID_LSTM_REC, st, tr_lstm_bwd(e, w.gates, w.cseq, w.dh, w.lstm_scratch, B, T, st));
+    VS_LAUNCH(e, KID_TR_LSTM_BWD, st, tr_lstm_bwd(e, w.gates, w.cseq, w.dh, w.lstm_scratch, B, T, st));
     {
         long long n = M * 2 * H;
         k_shift_h<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.hout, w.hprev, T, H, n);
@@ -169,14 +188,14 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
     }
     for (int d = 0; d < 2; ++d) {
         const float* da = w.gates + (size_t)d * 4 * H;     // [M][4H] view with row stride 8H
-        TR(e, st, tr_gemm(da, 1, 8 * H, w.hprev + (size_t)d * H, 2 * H, 1, g->w_hh[d], H, 4 * H, H, Mi, false, st));     // dW_hh = da^T h_prev
-        TR(e, st, tr_gemm(da, 1, 8 * H, w.xcat, 8 * F, 1, g->w_ih[d], KI, 4 * H, 8 * F, Mi, false, st));                  // dW_ih[:, :8F] = da^T X
-        TR(e, st, tr_gemm(w.dsum + (size_t)d * 4 * H, 1, 8 * H, emb, E, 1, g->w_ih[d] + 8 * F, KI, 4 * H, E, B, false, st)); // dW_ih[:, 8F:] = (sum_t da)^T emb
+        TRK(e, KID_TR_GEMM, st, tr_gemm(da, 1, 8 * H, w.hprev + (size_t)d * H, 2 * H, 1, g->w_hh[d], H, 4 * H, H, Mi, false, st));     // dW_hh = da^T h_prev
+        TRK(e, KID_TR_GEMM, st, tr_gemm(da, 1, 8 * H, w.xcat, 8 * F, 1, g->w_ih[d], KI, 4 * H, 8 * F, Mi, false, st));                  // dW_ih[:, :8F] = da^T X
+        TRK(e, KID_TR_GEMM, st, tr_gemm(w.dsum + (size_t)d * 4 * H, 1, 8 * H, emb, E, 1, g->w_ih[d] + 8 * F, KI, 4 * H, E, B, false, st)); // dW_ih[:, 8F:] = (sum_t da)^T emb
         TR(e, st, tr_colsum(da, 8 * H, Mi, 4 * H, g->b_ih[d], st));
         TR(e, st, cudaMemcpyAsync(g->b_hh[d], g->b_ih[d], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
     }
-    if (grad_emb) TR(e, st, tr_gemm(w.dsum, 8 * H, 1, e->wih_e, E, 1, grad_emb, E, B, E, 8 * H, false, st));          // d emb = (sum_t da) W_ih[:, 8F:]
-    TR(e, st, tr_gemm(w.gates, 8 * H, 1, e->wih_x, 8 * F, 1, w.dxcat, 8 * F, Mi, 8 * F, 8 * H, false, st));           // d X = da W_ih[:, :8F]
+    if (grad_emb) TRK(e, KID_TR_GEMM, st, tr_gemm(w.dsum, 8 * H, 1, e->wih_e, E, 1, grad_emb, E, B, E, 8 * H, false, st));          // d emb = (sum_t da) W_ih[:, 8F:]
+    TRK(e, KID_TR_GEMM, st, tr_gemm(w.gates, 8 * H, 1, e->wih_x, 8 * F, 1, w.dxcat, 8 * F, Mi, 8 * F, 8 * H, false, st));           // d X = da W_ih[:, :8F]
     // ---- cnn8 (64 -> 8, BN, act) backward
     TR(e, st, tr_bn_bwd_cols(act, w.dxcat, w.z7, w.stat + 7 * 256, e->bn_gamma[7], w.sums, w.dxcat, 8, F, M, e->num_sms, st));   // dxcat <- dz7 (in place)
     k_sums_to_grads<<<1, 64, 0, st>>>(w.sums, g->bn_gamma[7], g->bn_beta[7], 8);
@@ -190,10 +209,12 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
     // ---- cnn7 .. cnn1
     for (int l = 6; l >= 0; --l) {
         const ConvGeom cg = kConv[l];
-        TR(e, st, tr_bn_bwd_plane(act, w.G1, w.z[l], w.stat + l * 256, e->bn_gamma[l], w.sums, w.G2, F, Fp, M, e->num_sms, st));   // G2 = dz_l
+        const bool tc_dgrad = e->train_tc && l >= 1;
+        TRK(e, KID_TR_BN_BWD, st, tr_bn_bwd_plane(act, w.G1, w.z[l], w.stat + l * 256, e->bn_gamma[l], w.sums, w.G2, F, Fp, M, e->num_sms, st,
+                                                  tc_dgrad ? w.Dhi : nullptr, tc_dgrad ? w.Dlo : nullptr));   // G2 = dz_l (+ bf16 hi/lo)
         k_sums_to_grads<<<1, 64, 0, st>>>(w.sums, g->bn_gamma[l], g->bn_beta[l], 64);
         TR(e, st, cudaGetLastError());
-        TR(e, st, tr_bn_stats_plane(w.G2, w.sums, F, Fp, M, e->num_sms, st));
+        TRK(e, KID_TR_BN_STATS, st, tr_bn_stats_plane(w.G2, w.sums, F, Fp, M, e->num_sms, st));
         k_sum0_to_float<<<1, 64, 0, st>>>(w.sums, g->conv_b[l], 64);
         TR(e, st, cudaGetLastError());
         if (l == 0) {
@@ -201,10 +222,15 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
             TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[0], 64, 1, 7, st));
             break;
         }
-        TR(e, st, tr_bn_act_plane(act, w.z[l - 1], w.P, w.stat + (l - 1) * 256, F, Fp, M * Fp, st));  // a_{l-1}
-        TR(e, st, tr_conv_wgrad(w.P, w.G2, w.dwp, T, F, Fp, cg.kh, cg.kw, cg.dil, M, st));
+        TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l - 1], w.P, w.stat + (l - 1) * 256, F, Fp, M * Fp, st));  // a_{l-1}
+        TRK(e, KID_TR_WGRAD, st, tr_conv_wgrad(w.P, w.G2, w.dwp, T, F, Fp, cg.kh, cg.kw, cg.dil, M, st));
         TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[l], 64, 64, cg.kh * cg.kw, st));
-        TR(e, st, launch_conv_fp32_ex(e, l, w.G2, w.G1, e->conv_wT32[l], e->ones64, e->zeros64, VS_ACT_NONE, B, T, st));   // G1 = d a_{l-1}
+        if (e->train_tc) {   // G1 = d a_{l-1}: conv of dz_l with the flipped / transposed weights
+            int rc = tc_train_conv(e, l, true, w.Dhi, w.Dlo, e->zeros64, w.G1, B, T, 0, KID_TR_DGRAD, st);
+            if (rc != VS_OK) return rc;
+        } else {
+            TRK(e, KID_TR_DGRAD, st, launch_conv_fp32_ex(e, l, w.G2, w.G1, e->conv_wT32[l], e->ones64, e->zeros64, VS_ACT_NONE, B, T, st));
+        }
     }
     return VS_OK;
 }

@@ -10,10 +10,11 @@ cudaError_t tr_bn_stats_plane(const float* z, double* sums, int F, int Fp, long 
 cudaError_t tr_bn_stats_cols(const float* z, double* sums, int C, int F, long long nrows, int num_sms, cudaStream_t st);
 cudaError_t tr_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* stat, float* rmean, float* rvar,
                            long long* nb, float momentum, int C, cudaStream_t st);
-cudaError_t tr_bn_act_plane(int act, const float* z, float* a, const float* stat, int F, int Fp, long long npix, cudaStream_t st);
+cudaError_t tr_bn_act_plane(int act, const float* z, float* a, const float* stat, int F, int Fp, long long npix, cudaStream_t st,
+                            elt16* ahi = nullptr, elt16* alo = nullptr, int elt = 1);
 cudaError_t tr_bn_act_cols(int act, const float* z, float* a, const float* stat, int C, int F, long long nrows, cudaStream_t st);
 cudaError_t tr_bn_bwd_plane(int act, const float* da, const float* z, const float* stat, const float* gamma, double* sums, float* dz,
-                            int F, int Fp, long long nrows, int num_sms, cudaStream_t st);
+                            int F, int Fp, long long nrows, int num_sms, cudaStream_t st, elt16* dhi = nullptr, elt16* dlo = nullptr);
 cudaError_t tr_bn_bwd_cols(int act, const float* da, const float* z, const float* stat, const float* gamma, double* sums, float* dz,
                            int C, int F, long long nrows, int num_sms, cudaStream_t st);
 cudaError_t tr_conv_wgrad(const float* a, const float* dz, float* dwp, int T, int F, int Fp, int kh, int kw, int dil, long long nrows, cudaStream_t st);

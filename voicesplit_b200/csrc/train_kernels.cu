@@ -89,7 +89,8 @@ __global__ void k_bn_finalize(const double* __restrict__ sums, double count, con
 
 // a = act(z * scale + shift), pads zeroed (plane) / cols layout
 template <int ACT>
-__global__ void __launch_bounds__(256) k_bn_act_plane(const float* __restrict__ z, float* __restrict__ a, const float* __restrict__ stat, int F, int Fp, long long n4) {
+__global__ void __launch_bounds__(256) k_bn_act_plane(const float* __restrict__ z, float* __restrict__ a, const float* __restrict__ stat, int F, int Fp, long long n4,
+                                                      elt16* __restrict__ ahi, elt16* __restrict__ alo, int elt) {
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // float4 index
     if (i >= n4) return;
     int c4 = (int)(i & 15) * 4;
@@ -103,6 +104,13 @@ __global__ void __launch_bounds__(256) k_bn_act_plane(const float* __restrict__ 
         o.z = activate<ACT>(fmaf(v.z, sc[2], sh[2])); o.w = activate<ACT>(fmaf(v.w, sc[3], sh[3]));
     }
     reinterpret_cast<float4*>(a)[i] = o;
+    if (ahi) {   // also as 16-bit hi/lo planes: the operand of the tensor-core conv
+        __align__(8) elt16 h[4], l[4];
+        split16_rt(o.x, elt, h[0], l[0]); split16_rt(o.y, elt, h[1], l[1]);
+        split16_rt(o.z, elt, h[2], l[2]); split16_rt(o.w, elt, h[3], l[3]);
+        reinterpret_cast<uint2*>(ahi)[i] = *reinterpret_cast<const uint2*>(h);
+        reinterpret_cast<uint2*>(alo)[i] = *reinterpret_cast<const uint2*>(l);
+    }
 }
 template <int ACT>
 __global__ void __launch_bounds__(256) k_bn_act_cols(const float* __restrict__ z, float* __restrict__ a, const float* __restrict__ stat, int C, int F, long long n) {
@@ -143,7 +151,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce_plane(const float* __rest
 template <int ACT>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply_plane(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ stat,
                                                             const float* __restrict__ gamma, const double* __restrict__ sums, double count,
-                                                            float* __restrict__ dz, int F, int Fp, long long npix) {
+                                                            float* __restrict__ dz, int F, int Fp, long long npix,
+                                                            elt16* __restrict__ dhi, elt16* __restrict__ dlo) {
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // element index over [pixels][64]
     if (i >= npix * 64) return;
     int c = (int)(i & 63);
@@ -157,6 +166,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_plane(const float* __restr
         o = gamma[c] * rstd * (du - (float)(sums[c] / count) - xh * (float)(sums[64 + c] / count));
     }
     dz[i] = o;
+    if (dhi) {   // bf16 hi/lo (fp32 exponent range: gradients need no loss scaling) for the tensor-core data gradient
+        elt16 h, l;
+        split16<0>(o, h, l);
+        dhi[i] = h; dlo[i] = l;
+    }
 }
 template <int ACT>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce_cols(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ stat,
@@ -532,11 +546,12 @@ cudaError_t tr_bn_finalize(const double* sums, double count, const float* gamma,
     k_bn_finalize<<<1, 64, 0, st>>>(sums, count, gamma, beta, stat, rmean, rvar, nb, momentum, C);
     return cudaGetLastError();
 }
-cudaError_t tr_bn_act_plane(int act, const float* z, float* a, const float* stat, int F, int Fp, long long npix, cudaStream_t st) {
+cudaError_t tr_bn_act_plane(int act, const float* z, float* a, const float* stat, int F, int Fp, long long npix, cudaStream_t st,
+                            elt16* ahi, elt16* alo, int elt) {
     long long n4 = npix * 16;
     unsigned grid = (unsigned)((n4 + 255) / 256);
-    VS_ACT_DISPATCH(act, (k_bn_act_plane<VS_ACT_MISH><<<grid, 256, 0, st>>>(z, a, stat, F, Fp, n4)),
-                    (k_bn_act_plane<VS_ACT_RELU><<<grid, 256, 0, st>>>(z, a, stat, F, Fp, n4)));
+    VS_ACT_DISPATCH(act, (k_bn_act_plane<VS_ACT_MISH><<<grid, 256, 0, st>>>(z, a, stat, F, Fp, n4, ahi, alo, elt)),
+                    (k_bn_act_plane<VS_ACT_RELU><<<grid, 256, 0, st>>>(z, a, stat, F, Fp, n4, ahi, alo, elt)));
     return cudaGetLastError();
 }
 cudaError_t tr_bn_act_cols(int act, const float* z, float* a, const float* stat, int C, int F, long long nrows, cudaStream_t st) {
@@ -547,7 +562,7 @@ cudaError_t tr_bn_act_cols(int act, const float* z, float* a, const float* stat,
     return cudaGetLastError();
 }
 cudaError_t tr_bn_bwd_plane(int act, const float* da, const float* z, const float* stat, const float* gamma, double* sums, float* dz,
-                            int F, int Fp, long long nrows, int num_sms, cudaStream_t st) {
+                            int F, int Fp, long long nrows, int num_sms, cudaStream_t st, elt16* dhi, elt16* dlo) {
     cudaError_t e = cudaMemsetAsync(sums, 0, 128 * sizeof(double), st);
     if (e != cudaSuccess) return e;
     int grid = (int)(nrows < (long long)num_sms * 8 ? nrows : (long long)num_sms * 8);
@@ -556,8 +571,8 @@ cudaError_t tr_bn_bwd_plane(int act, const float* da, const float* z, const floa
     const long long npix = nrows * Fp;
     const double count = (double)nrows * F;
     unsigned g2 = (unsigned)((npix * 64 + 255) / 256);
-    VS_ACT_DISPATCH(act, (k_bn_bwd_apply_plane<VS_ACT_MISH><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix)),
-                    (k_bn_bwd_apply_plane<VS_ACT_RELU><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix)));
+    VS_ACT_DISPATCH(act, (k_bn_bwd_apply_plane<VS_ACT_MISH><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix, dhi, dlo)),
+                    (k_bn_bwd_apply_plane<VS_ACT_RELU><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix, dhi, dlo)));
     return cudaGetLastError();
 }
 cudaError_t tr_bn_bwd_cols(int act, const float* da, const float* z, const float* stat, const float* gamma, double* sums, float* dz,

@@ -150,6 +150,9 @@ class MaskEngine:
                         [f"lstm.{n}_l0{sfx}" for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")] +
                         ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"])
 
+    def set_train_tensor_cores(self, on):
+        _cabi.check(self.lib.vs_engine_set_train_tensor_cores(self.handle, 1 if on else 0), "vs_engine_set_train_tensor_cores")
+
     def train_forward(self, x, emb, bn_buffers=None, momentum=0.1):
         """Forward in BatchNorm-training mode.  bn_buffers: {state_dict key: tensor} of the running_mean /
         running_var / num_batches_tracked buffers to update in place (or None).  Returns (mask, saved)."""
@@ -224,14 +227,15 @@ class MaskEngine:
 
     KERNEL_NAMES = {0: "cnn1", 1: "cnn2", 2: "cnn3", 3: "cnn4", 4: "cnn5", 5: "cnn6", 6: "cnn7", 7: "cnn8_reshape",
                     8: "dvector_gate_bias", 9: "lstm_input_proj", 10: "lstm_recurrence", 11: "fc1", 12: "fc2_sigmoid_mask",
-                    13: "convert", 14: "head"}
+                    13: "convert", 14: "head", 20: "train_conv_fwd", 21: "train_bn_stats", 22: "train_bn_act", 23: "train_bn_bwd",
+                    24: "train_wgrad", 25: "train_dgrad", 26: "train_gemm", 27: "train_lstm_bwd", 28: "train_misc"}
 
     def set_profiling(self, on):
         _cabi.check(self.lib.vs_engine_set_profiling(self.handle, 1 if on else 0), "vs_engine_set_profiling")
 
     def profile_read(self):
         """[(kernel name, milliseconds)] of the last forward (profiling must be enabled)."""
-        ids = (ctypes.c_int32 * 64)()
-        ms = (ctypes.c_float * 64)()
-        n = self.lib.vs_profile_read(self.handle, 64, ids, ms)
+        ids = (ctypes.c_int32 * 256)()
+        ms = (ctypes.c_float * 256)()
+        n = self.lib.vs_profile_read(self.handle, 256, ids, ms)
         return [(self.KERNEL_NAMES.get(ids[i], str(ids[i])), float(ms[i])) for i in range(n)]

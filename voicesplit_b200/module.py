@@ -59,6 +59,7 @@ class _MaskTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, emb, *params):
         eng = module._sync_engine(x.device)
+        eng.set_train_tensor_cores(module.train_tensor_cores)
         buffers = {k: v for k, v in module.named_buffers()}
         mask, saved = eng.train_forward(x, emb, buffers, momentum=0.1)
         ctx.eng, ctx.saved = eng, saved
@@ -91,6 +92,8 @@ class MaskEstimator(nn.Module):
         # arithmetic of the contractions: "fp16x3" / "bf16x3" (fp32-faithful split operands on tensor
         # cores), "fp16" / "bf16" (single pass, fast) or "fp32" (CUDA cores); see include/voicesplit_b200.h
         self.precision = os.environ.get("VOICESPLIT_PRECISION", "fp16x3")
+        # training: conv forward / data gradient on tensor cores (fp16x3 / bf16x3); False = fp32 CUDA cores
+        self.train_tensor_cores = os.environ.get("VOICESPLIT_TRAIN_FP32", "0") != "1"
         self._engine = None
         self._packed_sig = None
 
