@@ -46,13 +46,29 @@ def main():
     target = torch.rand(B, T, F, device=dev) * x
     lengths = torch.full((B,), T * F, device=dev)
 
-    def step():
+    sections = {}
+
+    def mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def step(timed=False):
+        t0 = mark()
         opt.zero_grad(set_to_none=True)
         mask = model(x, emb)
+        t1 = mark()
         loss = si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths)
         loss.backward()
+        t2 = mark()
         n = vdist.allreduce_gradients(model.parameters(), dist)
+        t3 = mark()
         opt.step()
+        t4 = mark()
+        if timed:
+            torch.cuda.synchronize()
+            for name, a, b in (("forward", t0, t1), ("loss+backward", t1, t2), ("allreduce", t2, t3), ("adam", t3, t4)):
+                sections[name] = sections.get(name, 0.0) + a.elapsed_time(b)
         return loss, n
 
     for _ in range(args.warmup):
@@ -78,15 +94,19 @@ def main():
     losses = []
     for _ in range(args.steps):
         loss, nred = step()
-        losses.append(float(loss.detach()))
+        losses.append(loss.detach())
+    losses = [float(v) for v in losses]
     e1.record()
     torch.cuda.synchronize()
     thr, ms = vdist.aggregate_throughput(B * args.steps, e0.elapsed_time(e1), dist, dev)
+    for _ in range(2):
+        step(timed=True)
     if rank == 0:
         out = {"metric": "training utterances/s (forward + Si-SNR-PIT + backward + grad all-reduce + Adam)", "value": thr,
                "n_gpus": world, "per_gpu_batch": B, "frames": T, "freq_bins": F, "ms_per_step": ms / args.steps,
                "allreduce_floats": nred, "losses": losses, "arithmetic": "fp32 CUDA cores (training path)",
-               "bn_statistics": "per rank", "kernel_ms": breakdown}
+               "bn_statistics": "per rank", "kernel_ms": breakdown,
+               "section_ms": {k: round(v / 2, 2) for k, v in sections.items()}}
         if args.cpu_reference:
             from oracle import torch_port
             sd = {k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()}

@@ -124,6 +124,60 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, const __grid
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// MN-major operands (the weight-gradient GEMM contracts over PIXELS, which are the smem rows):
+//   D[128][64] = sum_k A[k][m] * B[k][n],  A rows m < 64 read strip row (k + shift), m >= 64 read strip row
+//   (k + shift + 1): the second 64-wide MN block of A is the same strip one pixel later, addressed through the
+//   descriptor's leading byte offset (= 128 B).  Tiles are [rows][64] 16-bit, 128-byte swizzle, filled by TMA.
+struct ProbeMnArgs {
+    float* D;          // [128][64]
+    int shift, K;      // K multiple of 16, <= 64
+    int lbo_bytes, sbo_bytes, swap;   // descriptor variants
+};
+__global__ void __launch_bounds__(128, 1) probe_mn_kernel(ProbeMnArgs a, const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;               // 128 rows x 128 B (strip: rows = pixels)
+    uint8_t* sB = smem + 16384;       // 136 rows x 128 B (dz tile: rows = pixels)
+    __shared__ uint64_t bar_load, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 64); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_load, (uint32_t)((128 + 136) * 128));
+        tma_load_2d(sA, &tmA, &bar_load, 0, 0);
+        tma_load_2d(sB, &tmB, &bar_load, 0, 0);
+    }
+    mbar_wait(&bar_load, 0);
+    if (tid == 0) {
+        // idesc: bf16 A/B, fp32 D, both MN-major
+        const uint32_t idesc = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+        tc_fence_after();
+        for (int k = 0; k < a.K / 16; ++k) {
+            uint32_t astart = smem_u32(sA) + (uint32_t)(a.shift + 16 * k) * 128;
+            uint32_t bstart = smem_u32(sB) + (uint32_t)(16 * k) * 128;
+            uint64_t da = a.swap ? make_smem_desc(astart, a.sbo_bytes, a.lbo_bytes, 2) : make_smem_desc(astart, a.lbo_bytes, a.sbo_bytes, 2);
+            uint64_t db = a.swap ? make_smem_desc(bstart, a.sbo_bytes, a.lbo_bytes, 2) : make_smem_desc(bstart, a.lbo_bytes, a.sbo_bytes, 2);
+            umma_bf16(tmem, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        int row = warp * 32 + (tid & 31);
+        for (int j = 0; j < 32; ++j) a.D[(size_t)row * 64 + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
 static float bf(float v) { return __bfloat162float(__float2bfloat16(v)); }
@@ -202,6 +256,40 @@ int main() {
         long long cyc;
         CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
         printf("PROBE %-32s cycles_per_mma=%.1f (ideal %d)\n", t.name, (double)cyc / (2000.0 * 4), t.N / 2);
+    }
+    // MN-major operands + two-tap M=128 through the leading byte offset (weight-gradient GEMM)
+    {
+        CUtensorMap tmAs, tmBs;
+        uint64_t dA2[2] = {64, 128}, sA2[1] = {128};
+        uint32_t bA2[2] = {64, 128};
+        uint64_t dB2[2] = {64, (uint64_t)strip}, sB2[1] = {128};
+        uint32_t bB2[2] = {64, 136};
+        if (!make_tmap_bf16(&tmAs, dA, 2, dA2, sA2, bA2, CU_TENSOR_MAP_SWIZZLE_128B) || !make_tmap_bf16(&tmBs, dB, 2, dB2, sB2, bB2, CU_TENSOR_MAP_SWIZZLE_128B)) {
+            printf("PROBE mn tensor map encode FAILED\n");
+            return 3;
+        }
+        CK(cudaFuncSetAttribute(probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        struct MnCase { const char* name; int shift, K, lbo, sbo, swap; };
+        for (const MnCase& c : {MnCase{"mn_K16_shift0_lbo128_sbo1024", 0, 16, 128, 1024, 0}, MnCase{"mn_K64_shift0_lbo128_sbo1024", 0, 64, 128, 1024, 0},
+                                MnCase{"mn_K64_shift2_lbo128_sbo1024", 2, 64, 128, 1024, 0}, MnCase{"mn_K64_shift5_lbo128_sbo1024", 5, 64, 128, 1024, 0},
+                                MnCase{"mn_K64_shift2_swapped", 2, 64, 128, 1024, 1}, MnCase{"mn_K64_shift0_lbo8192(same tap twice?)", 0, 64, 8192, 1024, 0}}) {
+            ProbeMnArgs a{dD, c.shift, c.K, c.lbo, c.sbo, c.swap};
+            CK(cudaMemset(dD, 0xff, 128 * 64 * 4));
+            probe_mn_kernel<<<1, 128, smem_bytes>>>(a, tmAs, tmBs);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("PROBE %-40s CUDA-ERROR %s\n", c.name, cudaGetErrorString(e)); return 4; }
+            CK(cudaMemcpy(hD.data(), dD, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+            double maxerr = 0, maxerr_lo = 0;
+            for (int m = 0; m < 128; ++m)
+                for (int n = 0; n < 64; ++n) {
+                    double s = 0;
+                    for (int k = 0; k < c.K; ++k) s += (double)hA[(k + c.shift + (m >= 64)) * 64 + (m & 63)] * hB[k * 64 + n];
+                    double d = fabs(s - hD[m * 64 + n]);
+                    if (!(d <= maxerr)) maxerr = d;
+                    if (m < 64 && !(d <= maxerr_lo)) maxerr_lo = d;
+                }
+            printf("PROBE %-40s max_err=%.3e (rows<64: %.3e) %s\n", c.name, maxerr, maxerr_lo, maxerr < 1e-3 ? "PASS" : "FAIL");
+        }
     }
     // accumulation behaviour: repeat the same K=64 product `it` times into one TMEM accumulator and compare
     // with it * (exact product): round-to-nearest accumulation errs like sqrt(steps) ulp with random sign,

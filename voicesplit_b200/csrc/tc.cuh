@@ -42,6 +42,10 @@ int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, con
 int tc_train_conv(vs_engine* e, int layer, bool dgrad, const elt16* in_hi, const elt16* in_lo, const float* shift, float* out32, int B, int T,
                   int elt, int kid, cudaStream_t st);
 
+// tc_wgrad.cu: weight gradient of layer 1..6 from bf16 hi/lo activation and dz planes; writes the reference layout
+int tc_train_wgrad(vs_engine* e, int layer, const elt16* a_hi, const elt16* a_lo, const elt16* d_hi, const elt16* d_lo, float* dwp,
+                   float* dw_out, int B, int T, int kid, cudaStream_t st);
+
 // ---- tc_lstm.cu: tensor-core recurrent kernel ---------------------------------------------------
 int tc_lstm_pack(vs_engine* e, void** slot, cudaStream_t st);
 void tc_lstm_destroy(void* slot);

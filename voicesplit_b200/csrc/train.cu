@@ -222,9 +222,15 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
             TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[0], 64, 1, 7, st));
             break;
         }
-        TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l - 1], w.P, w.stat + (l - 1) * 256, F, Fp, M * Fp, st));  // a_{l-1}
-        TRK(e, KID_TR_WGRAD, st, tr_conv_wgrad(w.P, w.G2, w.dwp, T, F, Fp, cg.kh, cg.kw, cg.dil, M, st));
-        TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[l], 64, 64, cg.kh * cg.kw, st));
+        if (e->train_tc) {   // a_{l-1} recomputed as bf16 hi/lo planes; weight gradient on tensor cores
+            TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l - 1], w.P, w.stat + (l - 1) * 256, F, Fp, M * Fp, st, w.Ahi, w.Alo, 0));
+            int rc = tc_train_wgrad(e, l, w.Ahi, w.Alo, w.Dhi, w.Dlo, w.dwp, g->conv_w[l], B, T, KID_TR_WGRAD, st);
+            if (rc != VS_OK) return rc;
+        } else {
+            TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l - 1], w.P, w.stat + (l - 1) * 256, F, Fp, M * Fp, st));  // a_{l-1}
+            TRK(e, KID_TR_WGRAD, st, tr_conv_wgrad(w.P, w.G2, w.dwp, T, F, Fp, cg.kh, cg.kw, cg.dil, M, st));
+            TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[l], 64, 64, cg.kh * cg.kw, st));
+        }
         if (e->train_tc) {   // G1 = d a_{l-1}: conv of dz_l with the flipped / transposed weights
             int rc = tc_train_conv(e, l, true, w.Dhi, w.Dlo, e->zeros64, w.G1, B, T, 0, KID_TR_DGRAD, st);
             if (rc != VS_OK) return rc;
