@@ -12,11 +12,16 @@ namespace vs {
 template <int ACT>
 __device__ __forceinline__ float act_grad(float u) {
     if (ACT == VS_ACT_RELU) return u > 0.f ? 1.f : 0.f;
-    // mish(u) = u * tanh(sp), sp = softplus(u) (identity above 20, utils/generic_utils.py:399 / F.softplus)
-    float sp = u > 20.f ? u : log1pf(expf(u));
-    float t = tanhf(sp);
-    float dsp = u > 20.f ? 1.f : 1.f / (1.f + expf(-u));   // d softplus / du = sigmoid(u)
-    return t + u * (1.f - t * t) * dsp;
+    // mish(u) = u * tanh(sp), sp = softplus(u) (identity above 20, utils/generic_utils.py:399 / F.softplus):
+    // d/du = t + u * (1 - t^2) * sigmoid(u).  With e = exp(u), n = (1+e)^2 - 1 = e(e+2):
+    // t = tanh(log(1+e)) = n / (n+2),  1 - t^2 = 4(n+1) / (n+2)^2,  sigmoid(u) = e / (1+e)  -> one exp, two divides
+    if (u > 20.f) return 1.f;            // t == 1 and 1 - t^2 == 0 in fp32 (and avoids e^2 overflow)
+    const float e = __expf(u);
+    const float n = e * (e + 2.f);
+    const float inv = __fdividef(1.f, n + 2.f);
+    const float t = n * inv;
+    const float sech2 = 4.f * (n + 1.f) * inv * inv;
+    return fmaf(u * sech2, __fdividef(e, 1.f + e), t);
 }
 
 // ---------------------------------------------------------------------------------------------
