@@ -118,8 +118,10 @@ def test_module_forward_matches_golden_and_repacks_after_update():
         m.fc2.bias.add_(3.0)
         mask2 = m(x, emb)
     assert (mask2 > mask).float().mean() > 0.99
-    with pytest.raises(NotImplementedError):
-        m.train()(x, emb)
+    out = m.train()(x, emb)                    # training mode: batch statistics, autograd graph attached
+    assert out.requires_grad and out.shape == x.shape
+    with pytest.raises(NotImplementedError):   # the gradient w.r.t. the spectrogram is not provided
+        m(x.clone().requires_grad_(True), emb)
 
 
 @pytest.mark.parametrize("precision", FAITHFUL)
