@@ -172,6 +172,25 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
                       const vs_grads* grads, float* grad_emb, int32_t B, int32_t T, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- audio front / back end (BASELINE config 5) --------------------------
+ * The reference's openVoiceFilterAudioProcessor.wav2spec / spec2wav with the mixture phase
+ * (utils/audio_processor.py:469-496): librosa.stft(n_fft, hop, win, hann, center, reflect) -> |D| -> dB ->
+ * clip-normalise to [0,1], and back through librosa.istft.  vs_audio_configure builds the (i)DFT operands
+ * for the given parameters (n_fft / 2 + 1 must equal num_freq).
+ *   vs_wav2spec: wav [B][L] fp32 device -> spec [B][T][F] in [0,1], phasor [B][T][F][2] = D / |D|, T = 1 + L / hop
+ *   vs_spec2wav: (masked) spec + phasor -> wav_out [B][hop * (T - 1)]
+ * A whole separation is  vs_wav2spec -> vs_forward (masked output) -> vs_spec2wav. */
+typedef struct vs_audio_params {
+    int32_t n_fft, hop_length, win_length;
+    float min_level_db, ref_level_db;   /* reference config.json:90-95: -100, 20 */
+} vs_audio_params;
+int vs_audio_configure(vs_engine* e, const vs_audio_params* params, void* stream);
+size_t vs_audio_workspace_bytes(const vs_engine* e, int32_t B, int32_t L);
+int vs_wav2spec(vs_engine* e, const float* wav, float* spec, float* phasor, int32_t B, int32_t L, void* workspace,
+                size_t workspace_bytes, void* stream);
+int vs_spec2wav(vs_engine* e, const float* spec, const float* phasor, float* wav_out, int32_t B, int32_t T,
+                void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test hooks: run a single conv layer l (0..6 -> 64-channel output) on an fp32 NCHW input
  * in [B][Cin][T][F] -> out [B][64][T][F], and the BiLSTM + head on a given conv_out.
  * They allocate internally and synchronise; not for the hot path. */

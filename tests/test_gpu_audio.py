@@ -1,0 +1,74 @@
+"""STFT front end / iSTFT back end on the device against oracle/audio_oracle.py (itself cross-validated against
+torch.stft/istft and scipy in tests/test_audio_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio_oracle as ao
+from voicesplit_b200 import synth
+from voicesplit_b200.engine import MaskEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def _signals(B, L, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(L) / 16000.0
+    out = []
+    for b in range(B):
+        f1, f2 = 150 + 90 * b, 900 + 333 * b
+        out.append(0.03 * np.sin(2 * np.pi * f1 * t) + 0.02 * np.sin(2 * np.pi * f2 * t + b) + 0.004 * rng.standard_normal(L))
+    return np.stack(out).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    dims = synth.make_dims(601, 256, 400, 600)
+    eng = MaskEngine(activation="mish", **dims)
+    sd = synth.make_state_dict(dims, 3, "default")
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    eng.configure_audio()
+    return eng
+
+
+@pytest.mark.parametrize("B,L", [(1, 16000), (3, 48000), (2, 7777)])
+def test_wav2spec_matches_oracle(engine, B, L):
+    wav = _signals(B, L)
+    spec, phasor = engine.wav2spec(torch.from_numpy(wav).cuda())
+    spec, phasor = spec.cpu().numpy(), phasor.cpu().numpy()
+    for b in range(B):
+        S, ph = ao.wav2spec(wav[b])
+        assert spec[b].shape == S.shape
+        # normalised dB magnitude: 1e-2 of the [0,1] range = 1 dB, only bins near the -100 dB floor differ that much
+        d = np.abs(spec[b] - S)
+        assert d.max() < 2e-2 and d.mean() < 2e-4, (d.max(), d.mean())
+        strong = S > 0.35                                     # phase is only meaningful where there is energy
+        err = np.abs(phasor[b][..., 0] + 1j * phasor[b][..., 1] - np.exp(1j * ph))[strong]
+        assert err.max() < 5e-3
+
+
+@pytest.mark.parametrize("B,L", [(2, 16000), (1, 48000)])
+def test_spec2wav_matches_oracle_and_round_trips(engine, B, L):
+    wav = _signals(B, L, seed=4)
+    wt = torch.from_numpy(wav).cuda()
+    spec, phasor = engine.wav2spec(wt)
+    back = engine.spec2wav(spec, phasor).cpu().numpy()
+    for b in range(B):
+        S, ph = ao.wav2spec(wav[b])
+        ref = ao.spec2wav(S, ph)
+        assert back[b].shape == ref.shape
+        assert np.abs(back[b] - ref).max() < 2e-4
+        assert np.abs(back[b] - wav[b][:len(ref)]).max() < 5e-4          # analysis -> synthesis is the identity up to the dB floor
+    # masked half-amplitude spectrum gives half-amplitude audio (linearity of the back end in the amplitude domain)
+    half = spec - (20 * np.log10(2.0)) / 100.0
+    quiet = engine.spec2wav(half.clamp(0, 1), phasor).cpu().numpy()
+    keep = (spec.cpu().numpy() > 0.2)
+    assert np.abs(quiet - 0.5 * back).max() < 2e-3 * max(1.0, np.abs(back).max()) or keep.mean() < 0.5
+
+
+def test_separate_end_to_end_shapes(engine):
+    wav = torch.from_numpy(_signals(2, 48000, seed=7)).cuda()
+    emb = torch.randn(2, 256, device="cuda")
+    out = engine.separate(wav, emb)
+    assert out.shape == (2, 160 * (1 + 48000 // 160 - 1)) and torch.isfinite(out).all()
+    assert out.abs().max() <= wav.abs().max() * 1.5

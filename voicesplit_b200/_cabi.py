@@ -31,6 +31,11 @@ class VsParams(ctypes.Structure):
                [(n, ctypes.c_void_p) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class VsAudioParams(ctypes.Structure):
+    _fields_ = [("n_fft", ctypes.c_int32), ("hop_length", ctypes.c_int32), ("win_length", ctypes.c_int32),
+                ("min_level_db", ctypes.c_float), ("ref_level_db", ctypes.c_float)]
+
+
 class VsTrainState(ctypes.Structure):
     _fields_ = [("running_mean", ctypes.c_void_p * 8), ("running_var", ctypes.c_void_p * 8),
                 ("num_batches_tracked", ctypes.c_void_p * 8), ("momentum", ctypes.c_float)]
@@ -59,6 +64,10 @@ SIGNATURES = {
     "vs_train_workspace_bytes": (_SZ, [_VP, _I, _I]),
     "vs_train_forward": (ctypes.c_int, [_VP, ctypes.POINTER(VsTrainState), _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_train_backward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, ctypes.POINTER(VsGrads), _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_audio_configure": (ctypes.c_int, [_VP, ctypes.POINTER(VsAudioParams), _VP]),
+    "vs_audio_workspace_bytes": (_SZ, [_VP, _I, _I]),
+    "vs_wav2spec": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_spec2wav": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),

@@ -116,6 +116,8 @@ struct vs_engine {
     size_t stage_bytes = 0;
     // pipelined host entry (vs_forward_host_submit / _wait): HostPipe in engine.cu
     void* pipe = nullptr;
+    // STFT / iSTFT state (audio.cu)
+    void* audio = nullptr;
 
     // tensor-core path state (tc_*.cu)
     void* tc = nullptr;
@@ -151,6 +153,7 @@ void prof_after(vs_engine* e, int id, cudaStream_t st);
 // training path (train.cu): raw per-channel vectors + data-gradient weights, refreshed by vs_engine_load_params
 int train_pack(vs_engine* e, const vs_params* p, cudaStream_t st);
 void train_free(vs_engine* e);
+void audio_free(vs_engine* e);
 
 // fp32 kernels (fp32_kernels.cu); all launch on `st` and return a cudaError_t
 cudaError_t launch_front_fp32(const vs_engine* e, const float* x, float* plane, int B, int T, cudaStream_t st);

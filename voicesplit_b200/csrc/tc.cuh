@@ -29,6 +29,35 @@ int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_i
 int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, const float* x, float* mask, int B, int T,
                        int precision, const TcLstmBuffers& lb, cudaStream_t st);
 
+// ---- tc_gemm.cu: the tensor-core GEMM (also used by audio.cu) -----------------------------------
+enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2, GEPI_PLAIN = 3, GEPI_STFT = 4 };
+
+struct GemmTcArgs {
+    int M, N, K;
+    int lda, ldw;               // row strides (elements) of the 16-bit A and W planes, multiples of 8
+    int n_tile, n_tiles_n, n_tiles_m, total_tiles, n_kb;
+    int passes, stages;
+    int group_rows;             // GATES: rows per utterance (T)
+    const float* bias;          // [N] (FC1/FC2) or null
+    const float* bias_group;    // [M / group_rows][N] (GATES)
+    float* out32;               // GATES: [M][N]; FC2: mask [M][N]
+    int ld_out;
+    elt16* out_hi;              // FC1: [M][ld16]
+    elt16* out_lo;
+    int ld16;
+    const float* xmul;          // FC2: spectrogram [M][N]
+    float* masked;              // FC2: optional
+    // STFT epilogue (audio.cu): out32 = normalised dB magnitude [utt][t_valid][n_bins], phasor = D / |D| as float2
+    float* phasor;
+    int rows_per_utt, t_valid, n_bins;
+    float min_db, ref_db;
+};
+// a.M/N/K, lda, ldw and the epilogue fields must be set; tile shape and pipeline depth are derived here
+int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt16* a_lo, const elt16* w_hi, const elt16* w_lo,
+                   GemmTcArgs a, int precision, cudaStream_t st);
+
+
+
 // ---- tc_gemm.cu: LSTM input projection / recurrence / FC head of the tensor-core path ------------
 int tc_gemm_pack(vs_engine* e, cudaStream_t st);
 void tc_gemm_destroy(vs_engine* e);

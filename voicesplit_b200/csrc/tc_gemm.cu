@@ -26,25 +26,6 @@ using namespace ptx;
 constexpr int kGemmEpiWarps = 8;
 constexpr int kChunkKb = 8;        // K blocks (of 64) accumulated in TMEM before promotion to registers
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
-enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2 };
-
-struct GemmTcArgs {
-    int M, N, K;
-    int lda, ldw;               // row strides (elements) of the 16-bit A and W planes, multiples of 8
-    int n_tile, n_tiles_n, n_tiles_m, total_tiles, n_kb;
-    int passes, stages;
-    int group_rows;             // GATES: rows per utterance (T)
-    const float* bias;          // [N] (FC1/FC2) or null
-    const float* bias_group;    // [M / group_rows][N] (GATES)
-    float* out32;               // GATES: [M][N]; FC2: mask [M][N]
-    int ld_out;
-    elt16* out_hi;              // FC1: [M][ld16]
-    elt16* out_lo;
-    int ld16;
-    const float* xmul;          // FC2: spectrogram [M][N]
-    float* masked;              // FC2: optional
-};
-
 template <int EPI, int ELT>
 __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a, const __grid_constant__ CUtensorMap tm_a_hi,
                                                              const __grid_constant__ CUtensorMap tm_a_lo,
@@ -186,6 +167,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                             for (int j = 0; j < 32; ++j)
                                 if (nbase + j < a.N && c0 + j < a.n_tile) dst[j] = acc[i][j] + bg[nbase + j];
                         }
+                    } else if (EPI == GEPI_PLAIN) {
+                        float* dst = a.out32 + (size_t)m * a.ld_out + nbase;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nbase + j < a.N && c0 + j < a.n_tile) dst[j] = acc[i][j];
+                    } else if (EPI == GEPI_STFT) {
+                        // columns are (re, im) pairs of DFT bin (nbase + j) / 2; row m = utterance * rows_per_utt + frame
+                        const int ub = m / a.rows_per_utt, t = m - ub * a.rows_per_utt;
+                        if (t < a.t_valid) {
+                            const size_t row = ((size_t)ub * a.t_valid + t) * a.n_bins;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const int k = (nbase + j) >> 1;
+                                if (k < a.n_bins && c0 + j < a.n_tile) {
+                                    const float re = acc[i][j], im = acc[i][j + 1];
+                                    const float mag = sqrtf(fmaf(re, re, im * im));
+                                    // utils/audio_processor.py:473-474,537-544: 20 log10(max(1e-5, |D|)) - ref, clip(S / -min, -1, 0) + 1
+                                    const float db = 20.f * log10f(fmaxf(1e-5f, mag)) - a.ref_db;
+                                    a.out32[row + k] = fminf(fmaxf(db / -a.min_db, -1.f), 0.f) + 1.f;
+                                    const float inv = mag > 0.f ? 1.f / mag : 0.f;
+                                    reinterpret_cast<float2*>(a.phasor)[row + k] = mag > 0.f ? make_float2(re * inv, im * inv) : make_float2(1.f, 0.f);
+                                }
+                            }
+                        }
                     } else if (EPI == GEPI_FC1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -321,8 +326,8 @@ static GemmWorkspace gemm_carve(const vs_engine* e, int B, int T, int precision,
 }
 size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision) { return gemm_carve(e, B, T, precision, nullptr).total; }
 
-static int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt16* a_lo, const elt16* w_hi, const elt16* w_lo,
-                          GemmTcArgs a, int precision, cudaStream_t st) {
+int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt16* a_lo, const elt16* w_hi, const elt16* w_lo,
+                   GemmTcArgs a, int precision, cudaStream_t st) {
     GemmState* g = g_state(e);
     a.passes = tc_passes(precision);
     const int elt = tc_elt(precision);
@@ -357,7 +362,9 @@ static int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, con
         ce = cudaFuncSetAttribute(k_gemm_tc<E, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
         if (ce == cudaSuccess) k_gemm_tc<E, L><<<grid, kGemmThreads, smem, st>>>(a, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo); \
     } while (0)
-    if (epi == GEPI_GATES) { if (elt) VS_GEMM_TC(GEPI_GATES, 1); else VS_GEMM_TC(GEPI_GATES, 0); }
+    if (epi == GEPI_PLAIN) { if (elt) VS_GEMM_TC(GEPI_PLAIN, 1); else VS_GEMM_TC(GEPI_PLAIN, 0); }
+    else if (epi == GEPI_STFT) { if (elt) VS_GEMM_TC(GEPI_STFT, 1); else VS_GEMM_TC(GEPI_STFT, 0); }
+    else if (epi == GEPI_GATES) { if (elt) VS_GEMM_TC(GEPI_GATES, 1); else VS_GEMM_TC(GEPI_GATES, 0); }
     else if (epi == GEPI_FC1) { if (elt) VS_GEMM_TC(GEPI_FC1, 1); else VS_GEMM_TC(GEPI_FC1, 0); }
     else { if (elt) VS_GEMM_TC(GEPI_FC2, 1); else VS_GEMM_TC(GEPI_FC2, 0); }
 #undef VS_GEMM_TC

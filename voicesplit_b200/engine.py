@@ -144,6 +144,52 @@ class MaskEngine:
                                                ctypes.c_void_p(st)), "vs_conv_stack")
         return out
 
+    # ---- audio front / back end (STFT -> normalised dB magnitude + phasor; iSTFT with that phase) ----------
+    def configure_audio(self, n_fft=1200, hop_length=160, win_length=400, min_level_db=-100.0, ref_level_db=20.0):
+        p = _cabi.VsAudioParams(n_fft, hop_length, win_length, min_level_db, ref_level_db)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_audio_configure(self.handle, ctypes.byref(p), ctypes.c_void_p(st)), "vs_audio_configure")
+        self.audio = dict(n_fft=n_fft, hop_length=hop_length, win_length=win_length)
+
+    def wav2spec(self, wav):
+        """wav [B, L] -> (spec [B, T, F] in [0,1], phasor [B, T, F, 2])   (reference wav2spec, audio_processor.py:469-476)"""
+        wav = wav.detach().to(torch.float32).contiguous()
+        B, L = wav.shape
+        T = 1 + L // self.audio["hop_length"]
+        F = self.dims["num_freq"]
+        with torch.cuda.device(wav.device):
+            need = int(self.lib.vs_audio_workspace_bytes(self.handle, B, L))
+            ws = torch.empty(need, dtype=torch.uint8, device=wav.device)
+            spec = torch.empty(B, T, F, dtype=torch.float32, device=wav.device)
+            phasor = torch.empty(B, T, F, 2, dtype=torch.float32, device=wav.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_wav2spec(self.handle, _ptr(wav), _ptr(spec), _ptr(phasor), B, L, _ptr(ws), need, ctypes.c_void_p(st)),
+                        "vs_wav2spec")
+        return spec, phasor
+
+    def spec2wav(self, spec, phasor):
+        """(masked) spec [B, T, F] + phasor -> wav [B, hop * (T - 1)]   (reference spec2wav with the mixture phase, :478-491)"""
+        spec = spec.detach().to(torch.float32).contiguous()
+        phasor = phasor.contiguous()
+        B, T, _ = spec.shape
+        Lout = self.audio["hop_length"] * (T - 1)
+        with torch.cuda.device(spec.device):
+            need = int(self.lib.vs_audio_workspace_bytes(self.handle, B, Lout))
+            ws = torch.empty(need, dtype=torch.uint8, device=spec.device)
+            wav = torch.empty(B, Lout, dtype=torch.float32, device=spec.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_spec2wav(self.handle, _ptr(spec), _ptr(phasor), _ptr(wav), B, T, _ptr(ws), need, ctypes.c_void_p(st)),
+                        "vs_spec2wav")
+        return wav
+
+    def separate(self, wav, emb, precision="fp16x3"):
+        """Waveform in, separated waveform out: STFT -> mask -> mask * spectrogram -> iSTFT with the mixture phase
+        (the reference's test path, utils/generic_utils.py:495-504)."""
+        spec, phasor = self.wav2spec(wav)
+        _, masked = self.forward(spec, emb, precision=precision, want_masked=True)
+        return self.spec2wav(masked, phasor)
+
     # ---- training (fp32, batch-statistics BatchNorm, full backward) ------------------------------
     PARAM_ORDER = tuple([k for l in range(8) for k in (f"conv.{CONV_IDX[l]}.weight", f"conv.{CONV_IDX[l]}.bias",
                                                         f"conv.{BN_IDX[l]}.weight", f"conv.{BN_IDX[l]}.bias")] +
