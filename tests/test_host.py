@@ -108,3 +108,14 @@ def test_synth_is_deterministic():
     x1, e1 = synth.make_inputs(2, 5, d, 9)
     x2, e2 = synth.make_inputs(2, 5, d, 9)
     assert np.array_equal(x1, x2) and np.array_equal(e1, e2) and x1.min() >= 0 and x1.max() <= 1
+
+
+def test_module_deepcopy_and_pickle_drop_the_engine_handle():
+    import copy
+    import pickle
+    m, _ = _model()
+    m._engine = object()          # stand-in for a live ctypes handle
+    c = copy.deepcopy(m)
+    assert c._engine is None and c._packed_sig is None
+    r = pickle.loads(pickle.dumps(m))
+    assert r._engine is None and list(r.state_dict()) == list(m.state_dict())

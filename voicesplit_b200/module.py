@@ -97,6 +97,13 @@ class MaskEstimator(nn.Module):
         self._engine = None
         self._packed_sig = None
 
+    # the engine handle is process-local: drop it when the module is pickled / deep-copied (it is rebuilt lazily)
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_packed_sig"] = None
+        return state
+
     # ---- engine plumbing ----------------------------------------------------------------------
     def _signature(self):
         sig = []
