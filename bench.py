@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--frames", type=int, default=601)
     ap.add_argument("--freq", type=int, default=257)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary config-4 / config-5 measurements")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -325,10 +326,71 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_throughput(dims, T, seconds_budget=20.0)
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_extras:
+            # secondary measurements (never the headline): BASELINE config 4 (training step) and config 5 (waveform in,
+            # separated waveform out) at the reference-native 301 x 601 shape; a failure here must not cost the headline
+            try:
+                del eng, x, emb, xh, eh, mask_h, masked_h, slots
+                torch.cuda.empty_cache()
+                line["extras"] = extra_measurements(dev)
+            except Exception as ex:      # noqa: BLE001
+                line["extras"] = {"error": repr(ex)[:300]}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def extra_measurements(dev):
+    from voicesplit_b200 import config as vconfig
+    from voicesplit_b200.engine import MaskEngine
+    from voicesplit_b200.losses import si_snr_with_pit
+    from models.voicesplit.model import VoiceSplit
+    out = {}
+    dims = synth.make_dims(601, 256, 400, 600)
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    # ---- config 4: forward (batch-stat BatchNorm) + Si-SNR-PIT + backward + Adam, B = 8, 301 x 601
+    model = VoiceSplit(vconfig.AttrDict(synth.make_config_dict(dims)))
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()})
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    B, T, F = 8, 301, 601
+    x, emb = synth.make_inputs(B, T, dims, 7)
+    x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
+    target = torch.rand(B, T, F, device=dev) * x
+    lengths = torch.full((B,), T * F, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        mask = model(x, emb)
+        si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths).backward()
+        opt.step()
+    ms = timed(step, 3)
+    out["train_step_config4"] = {"value": B / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "per_gpu_batch": B, "frames": T, "freq_bins": F,
+                                 "what": "forward (batch-stat BN) + Si-SNR-PIT + backward + Adam; conv fwd/dgrad/wgrad on tcgen05 (fp16x3/bf16x3), rest fp32"}
+    del model, opt
+    torch.cuda.empty_cache()
+    # ---- config 5: 3 s @ 16 kHz waveform -> STFT -> mask -> iSTFT -> waveform, B = 64
+    eng = MaskEngine(activation="mish", device=dev, **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(dims, 0, "stress").items() if v.dtype == np.float32})
+    eng.configure_audio()
+    Bw = 64
+    wav = torch.randn(Bw, 48000, device=dev) * 0.05
+    e2 = torch.randn(Bw, 256, device=dev)
+    ms = timed(lambda: eng.separate(wav, e2), 3)
+    out["audio_e2e_config5"] = {"value": Bw / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "batch": Bw, "samples": 48000,
+                                "what": "waveform -> STFT (tcgen05 GEMM) -> CNN+BiLSTM+FC mask (fp16x3) -> mask*spec -> iSTFT (mixture phase) -> waveform"}
+    return out
 
 
 def padded_f(F):
