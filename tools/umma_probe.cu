@@ -25,6 +25,7 @@ struct ProbeArgs {
     int base_offset_mode;     // 0: 0, 1: shift & 7, 2: (start_addr >> 7) & 7
     int iters;                // timing: repeat the 4-MMA group this many times
     long long* cycles;
+    int m_dim;                // MMA M (128 default, 64 for the half-height timing case)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, const __grid_constant__ CUtensorMap tmA,
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, const __grid
 
     long long t0 = 0, t1 = 0;
     if (tid == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, a.N);
+        const uint32_t idesc = make_idesc_bf16(a.m_dim ? a.m_dim : 128, a.N);
         const uint32_t aaddr = smem_u32(sA), baddr = smem_u32(sB);
         tc_fence_after();
         t0 = clock64();
@@ -313,6 +314,15 @@ int main() {
             }
         printf("PROBE accumulate_x%-5d mma_steps=%-5d mean_rel_err=%+.3e max_rel_err=%.3e frac_toward_zero=%.2f\n", iters, iters * 4,
                rel_sum / cnt, rel_max, toward_zero / cnt);
+    }
+    // does a half-height MMA (M = 64) take half the cycles?  (it would let the unpaired fifth filter tap run at M = 64)
+    for (int n : {256, 128}) {
+        ProbeArgs a{dA, dB, dD, n, strip, 0, 2, 0, 0, 2000, dcyc, 64};
+        probe_kernel<<<1, 128, smem_bytes>>>(a, tmA, tmB);
+        CK(cudaDeviceSynchronize());
+        long long cyc;
+        CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
+        printf("PROBE time_sw128_M64_N%-3d              cycles_per_mma=%.1f (M=128 takes %d)\n", n, (double)cyc / (2000.0 * 4), n / 2);
     }
     printf("PROBE done\n");
     return 0;
