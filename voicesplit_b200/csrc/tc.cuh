@@ -35,6 +35,7 @@ enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2, GEPI_PLAIN = 3, GEPI_STFT = 4
 struct GemmTcArgs {
     int M, N, K;
     int lda, ldw;               // row strides (elements) of the 16-bit A and W planes, multiples of 8
+    int tn;                     // 1: C[M][N] = sum_k A[k][m] * W[k][n] (both operands [K rows][cols], MN-major MMAs; N tile % 64 == 0)
     int n_tile, n_tiles_n, n_tiles_m, total_tiles, n_kb;
     int passes, stages;
     int group_rows;             // GATES: rows per utterance (T)
@@ -57,6 +58,12 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
                    GemmTcArgs a, int precision, cudaStream_t st);
 
 
+
+// training GEMMs on the tensor-core kernel (tc_gemm.cu)
+size_t tc_train_gemm_workspace_bytes(const vs_engine* e, int B, int T);
+int tc_train_inproj(vs_engine* e, const float* xcat, const float* bias_u, float* gates, void* ws, int B, int T, cudaStream_t st);
+int tc_train_lstm_input_grads(vs_engine* e, const float* da /*[M][8H]*/, const float* xcat, float* dxcat, float* dw_ih0, float* dw_ih1, int ld_dw,
+                              void* ws, int B, int T, cudaStream_t st);
 
 // ---- tc_gemm.cu: LSTM input projection / recurrence / FC head of the tensor-core path ------------
 int tc_gemm_pack(vs_engine* e, cudaStream_t st);

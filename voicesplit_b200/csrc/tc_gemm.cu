@@ -70,17 +70,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                     mbar_wait(&empty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&full[st], (uint32_t)(nplanes * (a_bytes + w_bytes)));
                     uint8_t* dst = smem + (size_t)st * stage_bytes;
-                    tma_load_2d(dst, &tm_a_hi, &full[st], kb * 64, mb * 128);
-                    if (nplanes == 2) tma_load_2d(dst + a_bytes, &tm_a_lo, &full[st], kb * 64, mb * 128);
-                    tma_load_2d(dst + nplanes * a_bytes, &tm_w_hi, &full[st], kb * 64, nb * a.n_tile);
-                    if (nplanes == 2) tma_load_2d(dst + nplanes * a_bytes + w_bytes_al, &tm_w_lo, &full[st], kb * 64, nb * a.n_tile);
+                    if (a.tn) {
+                        // operands are [K rows][cols]: 64-column blocks of 64 K-rows each (8 KB, one swizzle atom wide)
+                        for (int ib = 0; ib < 2; ++ib) {
+                            tma_load_2d(dst + ib * 8192, &tm_a_hi, &full[st], mb * 128 + ib * 64, kb * 64);
+                            if (nplanes == 2) tma_load_2d(dst + a_bytes + ib * 8192, &tm_a_lo, &full[st], mb * 128 + ib * 64, kb * 64);
+                        }
+                        for (int jb = 0; jb < a.n_tile / 64; ++jb) {
+                            tma_load_2d(dst + nplanes * a_bytes + jb * 8192, &tm_w_hi, &full[st], nb * a.n_tile + jb * 64, kb * 64);
+                            if (nplanes == 2)
+                                tma_load_2d(dst + nplanes * a_bytes + w_bytes_al + jb * 8192, &tm_w_lo, &full[st], nb * a.n_tile + jb * 64, kb * 64);
+                        }
+                    } else {
+                        tma_load_2d(dst, &tm_a_hi, &full[st], kb * 64, mb * 128);
+                        if (nplanes == 2) tma_load_2d(dst + a_bytes, &tm_a_lo, &full[st], kb * 64, mb * 128);
+                        tma_load_2d(dst + nplanes * a_bytes, &tm_w_hi, &full[st], kb * 64, nb * a.n_tile);
+                        if (nplanes == 2) tma_load_2d(dst + nplanes * a_bytes + w_bytes_al, &tm_w_lo, &full[st], kb * 64, nb * a.n_tile);
+                    }
                     if (++st == nst) { st = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, a.n_tile, ELT);
+            // TN: both operands MN-major; K step = 16 rows of 128 B, the 64-column blocks are 8 KB apart (LBO)
+            const uint32_t idesc = make_idesc_bf16(128, a.n_tile, ELT) | (a.tn ? ((1u << 15) | (1u << 16)) : 0u);
+            const uint32_t kstep = a.tn ? 2048u : 32u, lbo = a.tn ? 8192u : 16u;
             int st = 0, ph = 0, cc = 0;   // cc: chunk counter across tiles (TMEM buffer = cc & 1)
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 for (int kb0 = 0; kb0 < a.n_kb; kb0 += kChunkKb, ++cc) {
@@ -97,11 +112,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                         const uint32_t w_hi = a_hi + nplanes * a_bytes, w_lo = w_hi + w_bytes_al;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
+                            umma_bf16(d_tmem, make_smem_desc(a_hi + k * kstep, lbo, 1024, 2), make_smem_desc(w_hi + k * kstep, lbo, 1024, 2), idesc, accumulate);
                             accumulate = 1;
                             if (nplanes == 2) {
-                                umma_bf16(d_tmem, make_smem_desc(a_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
-                                umma_bf16(d_tmem, make_smem_desc(a_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
+                                umma_bf16(d_tmem, make_smem_desc(a_lo + k * kstep, lbo, 1024, 2), make_smem_desc(w_hi + k * kstep, lbo, 1024, 2), idesc, 1);
+                                umma_bf16(d_tmem, make_smem_desc(a_hi + k * kstep, lbo, 1024, 2), make_smem_desc(w_lo + k * kstep, lbo, 1024, 2), idesc, 1);
                             }
                         }
                         umma_commit(&empty[st]);
@@ -245,6 +260,16 @@ __global__ void k_absmax2(const float* __restrict__ w, long long n, unsigned int
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicMax(out, __float_as_uint(fabsf(w[i])));
 }
+// src [rows][cols] fp32 -> transposed [cols][rows] bf16 hi/lo
+__global__ void k_transpose_split_bf16(const float* __restrict__ src, int rows, int cols, elt16* __restrict__ hi, elt16* __restrict__ lo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * cols) return;
+    int r = (int)(i % rows);
+    long long c = i / rows;
+    elt16 h, l;
+    split16<0>(src[(size_t)r * cols + c], h, l);
+    hi[i] = h; lo[i] = l;
+}
 // fp32 [rows][cols] -> hi/lo planes of one element type (activations: conv_out in the debug hook)
 __global__ void k_split_rows(const float* __restrict__ src, long long n, int elt, elt16* __restrict__ hi, elt16* __restrict__ lo) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,6 +287,7 @@ struct GemmState {
     elt16 *wih_hi[2] = {}, *wih_lo[2] = {};  // [8H][8F]
     elt16 *fc1_hi[2] = {}, *fc1_lo[2] = {};  // [N1][2H]
     elt16 *fc2_hi[2] = {}, *fc2_lo[2] = {};  // [F][N1]
+    elt16 *wihT_hi = nullptr, *wihT_lo = nullptr;   // training: W_ih[:, :8F]^T as [8F][8H] bf16 (operand of dX = da W_ih)
     int max_smem = 0;
 };
 static GemmState* g_state(vs_engine* e);
@@ -286,6 +312,14 @@ int tc_gemm_pack(vs_engine* e, cudaStream_t st) {
         k_split_matrix<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(it.src, it.cols, it.rows, it.cols, ldo, nullptr, it.hi[0], it.lo[0],
                                                                     it.hi[1], it.lo[1]);
     }
+    {
+        const size_t n = (size_t)8 * F * 8 * H;
+        if (!g->wihT_hi) {
+            VS_CUDA_TRY(cudaMalloc(&g->wihT_hi, n * sizeof(elt16)));
+            VS_CUDA_TRY(cudaMalloc(&g->wihT_lo, n * sizeof(elt16)));
+        }
+        k_transpose_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->wih_x, 8 * H, 8 * F, g->wihT_hi, g->wihT_lo);
+    }
     VS_CUDA_TRY(cudaGetLastError());
     return VS_OK;
 }
@@ -297,6 +331,7 @@ void tc_gemm_destroy(vs_engine* e) {
         cudaFree(g->wih_hi[t]); cudaFree(g->wih_lo[t]); cudaFree(g->fc1_hi[t]); cudaFree(g->fc1_lo[t]);
         cudaFree(g->fc2_hi[t]); cudaFree(g->fc2_lo[t]);
     }
+    cudaFree(g->wihT_hi); cudaFree(g->wihT_lo);
     delete g;
 }
 
@@ -332,7 +367,8 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     a.passes = tc_passes(precision);
     const int elt = tc_elt(precision);
     a.n_tiles_n = (a.N + 255) / 256;
-    a.n_tile = (((a.N + a.n_tiles_n - 1) / a.n_tiles_n) + 15) / 16 * 16;
+    const int tile_q = a.tn ? 64 : 16;
+    a.n_tile = (((a.N + a.n_tiles_n - 1) / a.n_tiles_n) + tile_q - 1) / tile_q * tile_q;
     a.n_tiles_m = (a.M + 127) / 128;
     a.total_tiles = a.n_tiles_m * a.n_tiles_n;
     a.n_kb = (a.K + 63) / 64;
@@ -343,6 +379,10 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
         uint32_t ab[2] = {64, 128};
         uint64_t wd[2] = {(uint64_t)a.K, (uint64_t)a.N}, ws[1] = {(uint64_t)a.ldw * sizeof(elt16)};
         uint32_t wb[2] = {64, (uint32_t)a.n_tile};
+        if (a.tn) {   // [K rows][cols] operands: inner dimension = output rows / cols, boxes of 64 x 64
+            ad[0] = (uint64_t)a.M; ad[1] = (uint64_t)a.K; ab[1] = 64;
+            wd[0] = (uint64_t)a.N; wd[1] = (uint64_t)a.K; wb[1] = 64;
+        }
         bool ok = make_tmap_bf16(&tm_a_hi, (void*)a_hi, 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B);
         ok = ok && make_tmap_bf16(&tm_a_lo, (void*)(a_lo ? a_lo : a_hi), 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B);
         ok = ok && make_tmap_bf16(&tm_w_hi, (void*)w_hi, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -414,6 +454,68 @@ int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, con
         GemmTcArgs a{};
         a.M = M; a.N = F; a.K = N1; a.lda = (N1 + 7) / 8 * 8; a.ldw = (N1 + 7) / 8 * 8; a.bias = e->fc2_b; a.out32 = mask; a.ld_out = F; a.xmul = x; a.masked = masked;
         int rc = launch_gemm_tc(e, GEPI_FC2, KID_FC2, w.y_hi, w.y_lo, g->fc2_hi[elt], g->fc2_lo[elt], a, precision, st);
+        if (rc != VS_OK) return rc;
+    }
+    return VS_OK;
+}
+
+// ---- training GEMMs --------------------------------------------------------------------------------
+struct TrainGemmWs {
+    elt16 *x_hi, *x_lo;     // [M][8F]  LSTM input, fp16 (forward) then bf16 (backward)
+    elt16 *da_hi, *da_lo;   // [M][8H]  gate pre-activation gradients, bf16
+    size_t total;
+};
+static TrainGemmWs train_gemm_carve(const vs_engine* e, int B, int T, void* base) {
+    const int F = e->d.num_freq, H = e->d.lstm_dim;
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 1024); return r; };
+    const size_t M = (size_t)B * T;
+    TrainGemmWs w{};
+    w.x_hi = (elt16*)take(M * 8 * F * 2); w.x_lo = (elt16*)take(M * 8 * F * 2);
+    w.da_hi = (elt16*)take(M * 8 * H * 2); w.da_lo = (elt16*)take(M * 8 * H * 2);
+    w.total = off;
+    return w;
+}
+size_t tc_train_gemm_workspace_bytes(const vs_engine* e, int B, int T) { return train_gemm_carve(e, B, T, nullptr).total; }
+
+// gates_x = X W_ih[:, :8F]^T + bias_u (fp16x3)
+int tc_train_inproj(vs_engine* e, const float* xcat, const float* bias_u, float* gates, void* ws, int B, int T, cudaStream_t st) {
+    GemmState* g = g_state(e);
+    const int F = e->d.num_freq, H = e->d.lstm_dim;
+    TrainGemmWs w = train_gemm_carve(e, B, T, ws);
+    const long long n = (long long)B * T * 8 * F;
+    k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xcat, n, 1, w.x_hi, w.x_lo);
+    VS_LAUNCH(e, KID_CONVERT, st, cudaGetLastError());
+    GemmTcArgs a{};
+    a.M = B * T; a.N = 8 * H; a.K = 8 * F; a.lda = 8 * F; a.ldw = 8 * F; a.group_rows = T; a.bias_group = bias_u; a.out32 = gates; a.ld_out = 8 * H;
+    return launch_gemm_tc(e, GEPI_GATES, KID_INPROJ, w.x_hi, w.x_lo, g->wih_hi[1], g->wih_lo[1], a, VS_PREC_FP16X3, st);
+}
+
+// dX = da W_ih[:, :8F]  and  dW_ih[d][:, :8F] = da_d^T X  (bf16x3; the second contracts over tokens -> TN mode)
+int tc_train_lstm_input_grads(vs_engine* e, const float* da, const float* xcat, float* dxcat, float* dw_ih0, float* dw_ih1, int ld_dw,
+                              void* ws, int B, int T, cudaStream_t st) {
+    GemmState* g = g_state(e);
+    const int F = e->d.num_freq, H = e->d.lstm_dim, M = B * T;
+    TrainGemmWs w = train_gemm_carve(e, B, T, ws);
+    long long n = (long long)M * 8 * H;
+    k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(da, n, 0, w.da_hi, w.da_lo);
+    VS_LAUNCH(e, KID_CONVERT, st, cudaGetLastError());
+    n = (long long)M * 8 * F;
+    k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xcat, n, 0, w.x_hi, w.x_lo);
+    VS_LAUNCH(e, KID_CONVERT, st, cudaGetLastError());
+    {
+        GemmTcArgs a{};
+        a.M = M; a.N = 8 * F; a.K = 8 * H; a.lda = 8 * H; a.ldw = 8 * H; a.out32 = dxcat; a.ld_out = 8 * F;
+        int rc = launch_gemm_tc(e, GEPI_PLAIN, KID_TR_GEMM, w.da_hi, w.da_lo, g->wihT_hi, g->wihT_lo, a, VS_PREC_BF16X3, st);
+        if (rc != VS_OK) return rc;
+    }
+    float* outs[2] = {dw_ih0, dw_ih1};
+    for (int d = 0; d < 2; ++d) {
+        GemmTcArgs a{};
+        a.tn = 1;
+        a.M = 4 * H; a.N = 8 * F; a.K = M; a.lda = 8 * H; a.ldw = 8 * F; a.out32 = outs[d]; a.ld_out = ld_dw;
+        int rc = launch_gemm_tc(e, GEPI_PLAIN, KID_TR_GEMM, w.da_hi + (size_t)d * 4 * H, w.da_lo + (size_t)d * 4 * H, w.x_hi, w.x_lo, a, VS_PREC_BF16X3, st);
         if (rc != VS_OK) return rc;
     }
     return VS_OK;

@@ -58,6 +58,7 @@ struct TrainWs {
     float* dwp;             // packed conv weight gradient [25*64*64]
     float* dsum;            // [B][8H]
     float* lstm_scratch;    // forward exchange + backward exchange (max)
+    void* gemm_tc;          // 16-bit operand planes of the tensor-core GEMMs (tc_gemm.cu)
     unsigned int* barrier;
     size_t total;
 };
@@ -83,6 +84,7 @@ static TrainWs train_carve(const vs_engine* e, int B, int T, void* base) {
     size_t a = lstm_rec_scratch_bytes(e, B), b = tr_lstm_bwd_scratch_bytes(H, B);
     w.lstm_scratch = (float*)take(a > b ? a : b);
     w.barrier = (unsigned int*)take(256);
+    w.gemm_tc = take(tc_train_gemm_workspace_bytes(e, B, T));
     w.total = off;
     return w;
 }
@@ -142,7 +144,12 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
     TR(e, st, tr_bn_act_cols(act, w.z7, w.xcat, w.stat + 7 * 256, 8, F, M, st));
     // BiLSTM (gate activations and cell states are kept for the backward) and head
     VS_LAUNCH(e, KID_EMB_BIAS, st, launch_gemm_fp32(emb, E, e->wih_e, E, e->b_lstm, nullptr, 1, w.bias_u, 8 * H, B, 8 * H, E, false, EPI_NONE, nullptr, nullptr, st));
-    VS_LAUNCH(e, KID_INPROJ, st, launch_gemm_fp32(w.xcat, 8 * F, e->wih_x, 8 * F, nullptr, w.bias_u, T, w.gates, 8 * H, (int)M, 8 * H, 8 * F, false, EPI_NONE, nullptr, nullptr, st));
+    if (e->train_tc && (H % 4) == 0) {
+        int rc = tc_train_inproj(e, w.xcat, w.bias_u, w.gates, w.gemm_tc, B, T, st);
+        if (rc != VS_OK) return rc;
+    } else {
+        VS_LAUNCH(e, KID_INPROJ, st, launch_gemm_fp32(w.xcat, 8 * F, e->wih_x, 8 * F, nullptr, w.bias_u, T, w.gates, 8 * H, (int)M, 8 * H, 8 * F, false, EPI_NONE, nullptr, nullptr, st));
+    }
     VS_LAUNCH(e, KID_LSTM_REC, st, launch_lstm_rec_fp32(e, w.gates, w.hout, w.lstm_scratch, w.barrier, B, T, st, nullptr, nullptr, 0, w.gates, w.cseq));
     VS_LAUNCH(e, KID_FC1, st, launch_gemm_fp32(w.hout, 2 * H, e->fc1_w, 2 * H, e->fc1_b, nullptr, 1, w.y1, N1, (int)M, N1, 2 * H, true, EPI_RELU, nullptr, nullptr, st));
     VS_LAUNCH(e, KID_FC2, st, launch_gemm_fp32(w.y1, N1, e->fc2_w, N1, e->fc2_b, nullptr, 1, mask, F, (int)M, F, N1, false, EPI_SIGMOID_MASK, nullptr, nullptr, st));
@@ -186,16 +193,22 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
         k_sum_over_t<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w.gates, w.dsum, T, 8 * H, nb);
         TR(e, st, cudaGetLastError());
     }
+    const bool tc_gemms = e->train_tc && (H % 4) == 0;    // 16-byte operand rows for TMA
     for (int d = 0; d < 2; ++d) {
         const float* da = w.gates + (size_t)d * 4 * H;     // [M][4H] view with row stride 8H
         TRK(e, KID_TR_GEMM, st, tr_gemm(da, 1, 8 * H, w.hprev + (size_t)d * H, 2 * H, 1, g->w_hh[d], H, 4 * H, H, Mi, false, st));     // dW_hh = da^T h_prev
-        TRK(e, KID_TR_GEMM, st, tr_gemm(da, 1, 8 * H, w.xcat, 8 * F, 1, g->w_ih[d], KI, 4 * H, 8 * F, Mi, false, st));                  // dW_ih[:, :8F] = da^T X
+        if (!tc_gemms) TRK(e, KID_TR_GEMM, st, tr_gemm(da, 1, 8 * H, w.xcat, 8 * F, 1, g->w_ih[d], KI, 4 * H, 8 * F, Mi, false, st));  // dW_ih[:, :8F] = da^T X
         TRK(e, KID_TR_GEMM, st, tr_gemm(w.dsum + (size_t)d * 4 * H, 1, 8 * H, emb, E, 1, g->w_ih[d] + 8 * F, KI, 4 * H, E, B, false, st)); // dW_ih[:, 8F:] = (sum_t da)^T emb
         TR(e, st, tr_colsum(da, 8 * H, Mi, 4 * H, g->b_ih[d], st));
         TR(e, st, cudaMemcpyAsync(g->b_hh[d], g->b_ih[d], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
     }
     if (grad_emb) TRK(e, KID_TR_GEMM, st, tr_gemm(w.dsum, 8 * H, 1, e->wih_e, E, 1, grad_emb, E, B, E, 8 * H, false, st));          // d emb = (sum_t da) W_ih[:, 8F:]
-    TRK(e, KID_TR_GEMM, st, tr_gemm(w.gates, 8 * H, 1, e->wih_x, 8 * F, 1, w.dxcat, 8 * F, Mi, 8 * F, 8 * H, false, st));           // d X = da W_ih[:, :8F]
+    if (tc_gemms) {   // d X = da W_ih[:, :8F] and dW_ih[:, :8F] = da^T X on the tensor-core GEMM (bf16x3)
+        int rc = tc_train_lstm_input_grads(e, w.gates, w.xcat, w.dxcat, g->w_ih[0], g->w_ih[1], KI, w.gemm_tc, B, T, st);
+        if (rc != VS_OK) return rc;
+    } else {
+        TRK(e, KID_TR_GEMM, st, tr_gemm(w.gates, 8 * H, 1, e->wih_x, 8 * F, 1, w.dxcat, 8 * F, Mi, 8 * F, 8 * H, false, st));       // d X = da W_ih[:, :8F]
+    }
     // ---- cnn8 (64 -> 8, BN, act) backward
     TR(e, st, tr_bn_bwd_cols(act, w.dxcat, w.z7, w.stat + 7 * 256, e->bn_gamma[7], w.sums, w.dxcat, 8, F, M, e->num_sms, st));   // dxcat <- dz7 (in place)
     k_sums_to_grads<<<1, 64, 0, st>>>(w.sums, g->bn_gamma[7], g->bn_beta[7], 8);
