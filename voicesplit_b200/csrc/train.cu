@@ -135,7 +135,8 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
         TR(e, st, tr_bn_finalize(w.sums, (double)M * F, e->bn_gamma[l], e->bn_beta[l], w.stat + l * 256, bn ? bn->running_mean[l] : nullptr,
                                  bn ? bn->running_var[l] : nullptr, bn ? (long long*)bn->num_batches_tracked[l] : nullptr, mom, 64, st));
         const bool tc_next = e->train_tc && l < 6;     // the next layer's conv reads the 16-bit planes
-        TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l], w.P, w.stat + l * 256, F, Fp, M * Fp, st, tc_next ? w.Ahi : nullptr, tc_next ? w.Alo : nullptr, 1));
+        TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l], tc_next ? nullptr : w.P, w.stat + l * 256, F, Fp, M * Fp, st,
+                                                  tc_next ? w.Ahi : nullptr, tc_next ? w.Alo : nullptr, 1));
     }
     TR(e, st, launch_point8_fp32_ex(e, w.P, w.z7, e->conv_w32[7], e->ones64, e->conv_bias[7], VS_ACT_NONE, B, T, st));
     TR(e, st, tr_bn_stats_cols(w.z7, w.sums, 8, F, M, e->num_sms, st));
@@ -223,20 +224,26 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
     for (int l = 6; l >= 0; --l) {
         const ConvGeom cg = kConv[l];
         const bool tc_dgrad = e->train_tc && l >= 1;
-        TRK(e, KID_TR_BN_BWD, st, tr_bn_bwd_plane(act, w.G1, w.z[l], w.stat + l * 256, e->bn_gamma[l], w.sums, w.G2, F, Fp, M, e->num_sms, st,
-                                                  tc_dgrad ? w.Dhi : nullptr, tc_dgrad ? w.Dlo : nullptr));   // G2 = dz_l (+ bf16 hi/lo)
+        // tensor-core path: dz_l only as bf16 hi/lo planes (what wgrad and dgrad read); fp32 path: fp32 plane G2
+        TRK(e, KID_TR_BN_BWD, st, tr_bn_bwd_plane(act, w.G1, w.z[l], w.stat + l * 256, e->bn_gamma[l], w.sums, tc_dgrad ? nullptr : w.G2, F, Fp, M,
+                                                  e->num_sms, st, tc_dgrad ? w.Dhi : nullptr, tc_dgrad ? w.Dlo : nullptr));
         k_sums_to_grads<<<1, 64, 0, st>>>(w.sums, g->bn_gamma[l], g->bn_beta[l], 64);
         TR(e, st, cudaGetLastError());
-        TRK(e, KID_TR_BN_STATS, st, tr_bn_stats_plane(w.G2, w.sums, F, Fp, M, e->num_sms, st));
-        k_sum0_to_float<<<1, 64, 0, st>>>(w.sums, g->conv_b[l], 64);
-        TR(e, st, cudaGetLastError());
+        if (tc_dgrad) {
+            // a conv bias in front of a BatchNorm has an exactly zero gradient (sum dz = -gamma rstd S2 sum(xhat) / N, sum(xhat) = 0)
+            TR(e, st, cudaMemsetAsync(g->conv_b[l], 0, 64 * sizeof(float), st));
+        } else {
+            TRK(e, KID_TR_BN_STATS, st, tr_bn_stats_plane(w.G2, w.sums, F, Fp, M, e->num_sms, st));
+            k_sum0_to_float<<<1, 64, 0, st>>>(w.sums, g->conv_b[l], 64);
+            TR(e, st, cudaGetLastError());
+        }
         if (l == 0) {
             TR(e, st, tr_front_wgrad(x, w.G2, w.dwp, F, Fp, M, e->num_sms, st));
             TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[0], 64, 1, 7, st));
             break;
         }
         if (e->train_tc) {   // a_{l-1} recomputed as bf16 hi/lo planes; weight gradient on tensor cores
-            TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l - 1], w.P, w.stat + (l - 1) * 256, F, Fp, M * Fp, st, w.Ahi, w.Alo, 0));
+            TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l - 1], nullptr, w.stat + (l - 1) * 256, F, Fp, M * Fp, st, w.Ahi, w.Alo, 0));
             int rc = tc_train_wgrad(e, l, w.Ahi, w.Alo, w.Dhi, w.Dlo, w.dwp, g->conv_w[l], B, T, KID_TR_WGRAD, st);
             if (rc != VS_OK) return rc;
         } else {

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_bn_act_plane(const float* __restrict__ 
         o.x = activate<ACT>(fmaf(v.x, sc[0], sh[0])); o.y = activate<ACT>(fmaf(v.y, sc[1], sh[1]));
         o.z = activate<ACT>(fmaf(v.z, sc[2], sh[2])); o.w = activate<ACT>(fmaf(v.w, sc[3], sh[3]));
     }
-    reinterpret_cast<float4*>(a)[i] = o;
+    if (a) reinterpret_cast<float4*>(a)[i] = o;
     if (ahi) {   // also as 16-bit hi/lo planes: the operand of the tensor-core conv
         __align__(8) elt16 h[4], l[4];
         split16_rt(o.x, elt, h[0], l[0]); split16_rt(o.y, elt, h[1], l[1]);
@@ -132,25 +132,39 @@ __global__ void __launch_bounds__(256) k_bn_act_cols(const float* __restrict__ z
 template <int ACT>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce_plane(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ stat,
                                                              double* __restrict__ sums, int F, int Fp, long long nrows) {
-    const int c = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
-    const float mean = stat[c], rstd = stat[64 + c], sc = stat[128 + c], sh = stat[192 + c];
-    double s1 = 0.0, s2 = 0.0;
+    // thread = 4 channels (float4) x every 16th pixel of a row; block-level reduction, then one double atomic per channel
+    const int c4 = (threadIdx.x & 15) * 4, plane_lane = threadIdx.x >> 4;
+    float mean[4], rstd[4], sc[4], sh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { mean[k] = stat[c4 + k]; rstd[k] = stat[64 + c4 + k]; sc[k] = stat[128 + c4 + k]; sh[k] = stat[192 + c4 + k]; }
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const size_t base = (size_t)row * Fp * 64;
-        float f1 = 0.f, f2 = 0.f;
-        for (int f = lane4; f < F; f += 4) {
-            float zv = z[base + (size_t)f * 64 + c];
-            float du = da[base + (size_t)f * 64 + c] * act_grad<ACT>(fmaf(zv, sc, sh));
-            f1 += du; f2 = fmaf(du, (zv - mean) * rstd, f2);
+#pragma unroll 4
+        for (int f = plane_lane; f < F; f += 16) {
+            const float4 zv = *reinterpret_cast<const float4*>(z + base + (size_t)f * 64 + c4);
+            const float4 dv = *reinterpret_cast<const float4*>(da + base + (size_t)f * 64 + c4);
+            const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float du = dd[k] * act_grad<ACT>(fmaf(zz[k], sc[k], sh[k]));
+                s1[k] += du; s2[k] = fmaf(du, (zz[k] - mean[k]) * rstd[k], s2[k]);
+            }
         }
-        s1 += f1; s2 += f2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { d1[k] += s1[k]; d2[k] += s2[k]; s1[k] = 0.f; s2[k] = 0.f; }
     }
-    __shared__ double shm[2][256];
-    shm[0][threadIdx.x] = s1; shm[1][threadIdx.x] = s2;
+    __shared__ double shm[2][16][64];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { shm[0][plane_lane][c4 + k] = d1[k]; shm[1][plane_lane][c4 + k] = d2[k]; }
     __syncthreads();
-    if (threadIdx.x < 64) {
-        atomicAdd(&sums[c], shm[0][c] + shm[0][c + 64] + shm[0][c + 128] + shm[0][c + 192]);
-        atomicAdd(&sums[64 + c], shm[1][c] + shm[1][c + 64] + shm[1][c + 128] + shm[1][c + 192]);
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+        double t = 0.0;
+#pragma unroll
+        for (int l = 0; l < 16; ++l) t += shm[which][l][c];
+        atomicAdd(&sums[which * 64 + c], t);
     }
 }
 template <int ACT>
@@ -158,23 +172,31 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_plane(const float* __restr
                                                             const float* __restrict__ gamma, const double* __restrict__ sums, double count,
                                                             float* __restrict__ dz, int F, int Fp, long long npix,
                                                             elt16* __restrict__ dhi, elt16* __restrict__ dlo) {
-    long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // element index over [pixels][64]
-    if (i >= npix * 64) return;
-    int c = (int)(i & 63);
-    int f = (int)((i >> 6) % Fp);
-    float o = 0.f;
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // float4 index over [pixels][16]
+    if (i >= npix * 16) return;
+    const int c4 = (int)(i & 15) * 4;
+    const int f = (int)((i >> 4) % Fp);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (f < F) {
-        const float mean = stat[c], rstd = stat[64 + c];
-        float zv = z[i];
-        float du = da[i] * act_grad<ACT>(fmaf(zv, stat[128 + c], stat[192 + c]));
-        float xh = (zv - mean) * rstd;
-        o = gamma[c] * rstd * (du - (float)(sums[c] / count) - xh * (float)(sums[64 + c] / count));
+        const float4 zv = reinterpret_cast<const float4*>(z)[i];
+        const float4 dv = reinterpret_cast<const float4*>(da)[i];
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c4 + k;
+            const float mean = stat[c], rstd = stat[64 + c];
+            const float du = dd[k] * act_grad<ACT>(fmaf(zz[k], stat[128 + c], stat[192 + c]));
+            const float xh = (zz[k] - mean) * rstd;
+            o[k] = gamma[c] * rstd * (du - (float)(sums[c] / count) - xh * (float)(sums[64 + c] / count));
+        }
     }
-    dz[i] = o;
+    if (dz) reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
     if (dhi) {   // bf16 hi/lo (fp32 exponent range: gradients need no loss scaling) for the tensor-core data gradient
-        elt16 h, l;
-        split16<0>(o, h, l);
-        dhi[i] = h; dlo[i] = l;
+        __align__(8) elt16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split16<0>(o[k], h[k], l[k]);
+        reinterpret_cast<uint2*>(dhi)[i] = *reinterpret_cast<const uint2*>(h);
+        reinterpret_cast<uint2*>(dlo)[i] = *reinterpret_cast<const uint2*>(l);
     }
 }
 template <int ACT>
@@ -575,7 +597,7 @@ cudaError_t tr_bn_bwd_plane(int act, const float* da, const float* z, const floa
                     (k_bn_bwd_reduce_plane<VS_ACT_RELU><<<grid, 256, 0, st>>>(da, z, stat, sums, F, Fp, nrows)));
     const long long npix = nrows * Fp;
     const double count = (double)nrows * F;
-    unsigned g2 = (unsigned)((npix * 64 + 255) / 256);
+    unsigned g2 = (unsigned)((npix * 16 + 255) / 256);
     VS_ACT_DISPATCH(act, (k_bn_bwd_apply_plane<VS_ACT_MISH><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix, dhi, dlo)),
                     (k_bn_bwd_apply_plane<VS_ACT_RELU><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix, dhi, dlo)));
     return cudaGetLastError();
