@@ -200,6 +200,12 @@ int vs_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, co
                        float* lstm_out, float* mask, int32_t B, int32_t T, int32_t precision,
                        void* stream);
 
+/* Phase timers of the last tensor-core LSTM recurrence (SM cycles summed over all steps, CTA 0):
+ * [0] producer waits on the group barrier, [1] producer issues TMA, [2] MMA thread waits for h blocks,
+ * [3] MMA issue, [4] cell thread waits for the accumulator, [5] TMEM load + gate math, [6] stores,
+ * [7] CTA barrier + fence + atomic.  Synchronises the device. */
+int vs_debug_lstm_timing(vs_engine* e, int64_t* cycles8);
+
 /* Number of kernels this library launched during the last vs_forward / vs_conv_stack. */
 int vs_last_launch_count(const vs_engine* e);
 

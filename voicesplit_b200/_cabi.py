@@ -71,6 +71,7 @@ SIGNATURES = {
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "vs_debug_lstm_timing": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int64)]),
     "vs_last_launch_count": (ctypes.c_int, [_VP]),
     "vs_engine_set_profiling": (ctypes.c_int, [_VP, _I]),
     "vs_profile_read": (ctypes.c_int, [_VP, _I, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)]),

@@ -499,6 +499,11 @@ int vs_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, co
     return ret;
 }
 
+int vs_debug_lstm_timing(vs_engine* e, int64_t* cycles8) {
+    if (!e || !cycles8) { set_error("null argument"); return VS_ERR_INVALID; }
+    return tc_lstm_read_timing(tc_lstm_slot(e), (long long*)cycles8);
+}
+
 int vs_last_launch_count(const vs_engine* e) { return e ? e->launches : 0; }
 
 int vs_engine_set_profiling(vs_engine* e, int32_t enabled) {

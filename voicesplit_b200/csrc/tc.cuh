@@ -89,6 +89,7 @@ size_t tc_lstm_scratch_bytes(const vs_engine* e, int B);
 int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* hout, void* scratch, elt16* hr_hi, elt16* hr_lo,
                        int B, int T, int precision, cudaStream_t st);
 void* tc_lstm_slot(vs_engine* e);  // LstmState pointer kept in TcState (tc_conv.cu)
+int tc_lstm_read_timing(void* slot, long long* out8);
 
 cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
                              elt16* xlo, int ldx, int B, int T, cudaStream_t st);

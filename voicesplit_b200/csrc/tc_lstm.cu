@@ -33,7 +33,12 @@ struct LstmTcArgs {
     elt16* hr_lo;
     unsigned int* barrier;        // [2][ngroups_total]
     int ngroups_total;
+    long long* timing;            // [8] cycle counters accumulated by CTA 0 (vs_debug_lstm_timing): see below
 };
+// timing[0] producer: spin on the group barrier     timing[1] producer: issuing TMA (incl. waiting for a free stage)
+// timing[2] MMA thread: waiting for h K-blocks      timing[3] MMA thread: issuing MMAs + commits
+// timing[4] cell thread 64: waiting for acc_full    timing[5] cell thread 64: TMEM load + gate math
+// timing[6] cell thread 64: stores                  timing[7] cell thread 64: bar.sync + fence + atomic
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
     // 1 / (1 + 2^(-x log2 e)) with the raw MUFU approximations (no range/denormal slow paths):
@@ -96,13 +101,17 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     tma_load_2d(w_smem + (size_t)(p * a.nkb + kb) * 8192, p == 0 ? &tm_w_hi : &tm_w_lo, w_full, kb * 64,
                                 (d * a.nslices + slice) * 64);
             int st = 0, ph = 0;
+            long long tm_spin = 0, tm_issue = 0;
             for (int s = 1; s < a.T; ++s) {
                 // wait until every slice of this (direction, group) has published h_{s-1}
                 const unsigned int target = (unsigned int)s * a.nslices;
                 unsigned int spins = 0;
+                const long long c0 = clock64();
                 while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
                     if (++spins > (1u << 28)) __trap();
                 }
+                const long long c1 = clock64();
+                tm_spin += c1 - c0;
                 __threadfence();
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy flag read -> async-proxy (TMA) data reads
                 const int par = (s - 1) & 1;                       // buffer h_{s-1} was written to
@@ -115,7 +124,9 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     if (nplanes == 2) tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
                     if (++st == kLStages) { st = 0; ph ^= 1; }
                 }
+                tm_issue += clock64() - c1;
             }
+            if (blockIdx.x == 0 && a.timing) { a.timing[0] = tm_spin; a.timing[1] = tm_issue; }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -125,10 +136,14 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
             tc_fence_after();
             const uint32_t w_addr = smem_u32(w_smem);
             int st = 0, ph = 0;
+            long long tm_wait = 0, tm_mma = 0;
             for (int s = 1; s < a.T; ++s) {
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < a.nkb; ++kb) {
+                    const long long c0 = clock64();
                     mbar_wait(&a_full[st], ph);
+                    const long long c1 = clock64();
+                    tm_wait += c1 - c0;
                     tc_fence_after();
                     const uint32_t h_hi = smem_u32(a_ring + (size_t)st * stage_bytes), h_lo = h_hi + 16384;
                     const uint32_t w_hi = w_addr + (uint32_t)kb * 8192, w_lo = w_addr + (uint32_t)(a.nkb + kb) * 8192;
@@ -142,9 +157,11 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     }
                     umma_commit(&a_empty[st]);
                     if (++st == kLStages) { st = 0; ph ^= 1; }
+                    tm_mma += clock64() - c1;
                 }
                 umma_commit(acc_full);
             }
+            if (blockIdx.x == 0 && a.timing) { a.timing[2] = tm_wait; a.timing[3] = tm_mma; }
         }
     } else {
         // ---------------- cell update: thread = one utterance, 16 units ----------------
@@ -157,6 +174,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
 #pragma unroll
         for (int j = 0; j < kLU; ++j) c[j] = 0.f;
         const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16);
+        long long tm_acc = 0, tm_math = 0, tm_store = 0, tm_bar = 0;
         for (int s = 0; s < a.T; ++s) {
             const int t = d ? a.T - 1 - s : s;
             // input projection for this step (issued before waiting on the MMA)
@@ -175,8 +193,11 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     for (int j = 0; j < kLU; ++j) gx[g][j] = j < nu ? __ldg(gsrc + (size_t)g * a.H + j) : 0.f;
                 }
             }
+            long long c0 = clock64();
             if (s > 0) {
                 mbar_wait(acc_full, (s - 1) & 1);
+                tm_acc += clock64() - c0;
+                c0 = clock64();
                 tc_fence_after();
                 uint32_t r0[32], r1[32];
                 tmem_ld_32x32(t_base, r0);
@@ -205,6 +226,11 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 hv[j] = og * tanh_fast(c[j]);
                 split16<ELT>(hv[j], vh[j], vl[j]);
                 split16<ELT>(fmaxf(hv[j], 0.f), rh[j], rl[j]);
+            }
+            {
+                const long long c1 = clock64();
+                tm_math += c1 - c0;
+                c0 = c1;
             }
             if (valid) {
                 if (nu == kLU && (a.H & 7) == 0) {
@@ -237,6 +263,11 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     }
                 }
             }
+            {
+                const long long c1 = clock64();
+                tm_store += c1 - c0;
+                c0 = c1;
+            }
             if (s + 1 < a.T) {
                 // publish h_s: the 128 cell threads meet at a CTA barrier, then ONE thread issues the
                 // gpu-scope release (cumulative over the stores ordered before the barrier) and bumps
@@ -246,8 +277,10 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     __threadfence();
                     atomicAdd(counter, 1u);
                 }
+                tm_bar += clock64() - c0;
             }
         }
+        if (blockIdx.x == 0 && threadIdx.x == 64 && a.timing) { a.timing[4] = tm_acc; a.timing[5] = tm_math; a.timing[6] = tm_store; a.timing[7] = tm_bar; }
     }
     tc_fence_before();
     __syncthreads();
@@ -271,6 +304,7 @@ __global__ void k_pack_whh_tc(const float* __restrict__ whh, int H, int Hp, int 
 
 struct LstmState {
     elt16 *w_hi[2] = {}, *w_lo[2] = {};
+    long long* timing = nullptr;
     int max_smem = 0;
 };
 
@@ -281,6 +315,7 @@ int tc_lstm_pack(vs_engine* e, void** slot, cudaStream_t st) {
         *slot = s;
     }
     LstmState* s = (LstmState*)*slot;
+    if (!s->timing) VS_CUDA_TRY(cudaMalloc(&s->timing, 8 * sizeof(long long)));
     const int H = e->d.lstm_dim, Hp = (H + 7) / 8 * 8, nslices = (H + kLU - 1) / kLU;
     const size_t n = (size_t)2 * nslices * 64 * Hp;
     for (int t = 0; t < 2; ++t) {
@@ -297,6 +332,7 @@ void tc_lstm_destroy(void* slot) {
     LstmState* s = (LstmState*)slot;
     if (!s) return;
     for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t]); cudaFree(s->w_lo[t]); }
+    cudaFree(s->timing);
     delete s;
 }
 
@@ -324,6 +360,7 @@ int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* ho
     a.barrier = (unsigned int*)(p + 2 * plane);
     a.hr_hi = hr_hi; a.hr_lo = passes == 3 ? hr_lo : nullptr;
     a.ngroups_total = ngroups_total;
+    a.timing = s->timing;
     if (2 * ngroups_total * (int)sizeof(unsigned int) > 4096) { set_error("batch too large for the LSTM barrier table"); return VS_ERR_INVALID; }
     const int nplanes = passes == 3 ? 2 : 1;
     const int smem = 1024 + nplanes * a.nkb * 8192 + kLStages * nplanes * 16384 + 256;
@@ -358,6 +395,12 @@ int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* ho
     }
     if (e->profiling) prof_after(e, KID_LSTM_REC, st);
     return VS_OK;
+}
+
+int tc_lstm_read_timing(void* slot, long long* out8) {
+    LstmState* s = (LstmState*)slot;
+    if (!s || !s->timing) return VS_ERR_STATE;
+    return cudaMemcpy(out8, s->timing, 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? VS_OK : VS_ERR_CUDA;
 }
 
 }  // namespace vs
