@@ -243,20 +243,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
 // cnn1 on CUDA cores, writing the bf16 hi/lo planes (K = 7, C_in = 1: not MMA-shaped)
 // ---------------------------------------------------------------------------------------------
 template <int ACT, int ELT>
-__global__ void __launch_bounds__(256) k_front_tc(const float* __restrict__ x, elt16* __restrict__ hi,
-                                                  elt16* __restrict__ lo, const float* __restrict__ w,
-                                                  const float* __restrict__ scale, const float* __restrict__ shift,
-                                                  int F, int Fp, int nrows) {
-    // one block per (utterance, frame) row; thread = 8 output channels x 2 adjacent pixels, its 56
-    // filter taps live in registers for the whole row
+__global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x, elt16* __restrict__ hi,
+                                                     elt16* __restrict__ lo, const float* __restrict__ w,
+                                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                                     int F, int Fp, int nrows) {
+    // one block per (utterance, frame) row; thread = 4 output channels x 2 adjacent pixels, its 28 filter taps
+    // live in registers for the whole row (4 channels keep the register count low enough for 3 blocks per SM:
+    // the kernel is bound by dependent-issue latency of the Mish / split epilogue, not by bandwidth)
     extern __shared__ float xs[];   // [Fp + 8]: x[f - 3] at xs[f]
-    const int tid = threadIdx.x, cg = tid & 7, pp = tid >> 3;
-    float wr[7][8], sc[8], sh[8];
+    const int tid = threadIdx.x, cg = tid & 15, pp = tid >> 4;
+    float wr[7][4], sc[4], sh[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        sc[c] = scale[cg * 8 + c]; sh[c] = shift[cg * 8 + c];
+    for (int c = 0; c < 4; ++c) {
+        sc[c] = scale[cg * 4 + c]; sh[c] = shift[cg * 4 + c];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) wr[j][c] = w[j * 64 + cg * 8 + c];
+        for (int j = 0; j < 7; ++j) wr[j][c] = w[j * 64 + cg * 4 + c];
     }
     for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
         const float* xrow = x + (size_t)row * F;
@@ -266,25 +267,25 @@ __global__ void __launch_bounds__(256) k_front_tc(const float* __restrict__ x, e
             xs[i] = (f >= 0 && f < F) ? xrow[f] : 0.f;
         }
         __syncthreads();
-        for (int f0 = pp * 2; f0 < Fp; f0 += 64) {
+        for (int f0 = pp * 2; f0 < Fp; f0 += 32) {
             float xv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) xv[i] = xs[f0 + i];
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const int f = f0 + p;
-                __align__(16) elt16 vh[8], vl[8];
+                __align__(8) elt16 vh[4], vl[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc = fmaf(wr[j][c], xv[p + j], acc);
                     float y = (f < F) ? act_fast<ACT>(fmaf(acc, sc[c], sh[c])) : 0.f;
                     split16<ELT>(y, vh[c], vl[c]);
                 }
-                const size_t o = ((size_t)row * Fp + f) * 64 + cg * 8;
-                *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(vh);
-                if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(vl);
+                const size_t o = ((size_t)row * Fp + f) * 64 + cg * 4;
+                *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(vh);
+                if (lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(vl);
             }
         }
     }
@@ -583,7 +584,7 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
 static cudaError_t launch_front_tc(const vs_engine* e, const float* x, elt16* hi, elt16* lo, int elt, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
     const int nrows = B * T;
-    const int grid = nrows < e->num_sms * 8 ? nrows : e->num_sms * 8;
+    const int grid = nrows < e->num_sms * 12 ? nrows : e->num_sms * 12;
     const size_t smem = (size_t)(Fp + 8) * sizeof(float);
 #define VS_FRONT(A, E) k_front_tc<A, E><<<grid, 256, smem, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], F, Fp, nrows)
     if (e->d.activation == VS_ACT_RELU) { if (elt) VS_FRONT(VS_ACT_RELU, 1); else VS_FRONT(VS_ACT_RELU, 0); }
