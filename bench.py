@@ -390,7 +390,41 @@ def extra_measurements(dev):
     ms = timed(lambda: eng.separate(wav, e2), 3)
     out["audio_e2e_config5"] = {"value": Bw / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "batch": Bw, "samples": 48000,
                                 "what": "waveform -> STFT (tcgen05 GEMM) -> CNN+BiLSTM+FC mask (fp16x3) -> mask*spec -> iSTFT (mixture phase) -> waveform"}
+    del eng, wav, e2
+    torch.cuda.empty_cache()
+    # ---- the honest GPU bar: the reference's own stock torch ops (restated in oracle/torch_port.py; the
+    # reference tree cannot travel) on the SAME B200 through cuDNN/cuBLAS eager, strict fp32 and TF32-allowed
+    out["stock_torch_gpu_baseline"] = stock_torch_gpu_baseline(dev)
     return out
+
+
+def stock_torch_gpu_baseline(dev, B=32, T=601):
+    from oracle import torch_port
+    dims = synth.make_dims(257, 256, 400, 600)
+    sd = {k: torch.from_numpy(np.array(v)).to(dev) for k, v in synth.make_state_dict(dims, 0, "stress").items()}
+    x, emb = synth.make_inputs(B, T, dims, 11)
+    x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
+    res = {"batch": B, "frames": T, "freq_bins": 257, "unit": "utterances/s",
+           "what": "stock PyTorch eager (F.conv2d/batch_norm/Mish/LSTM/linear -> cuDNN/cuBLAS) on the same GPU, inputs resident"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(2):
+                torch_port.forward(sd, x, emb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                torch_port.forward(sd, x, emb)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = B * 3 / (e0.elapsed_time(e1) / 1e3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return res
 
 
 def padded_f(F):

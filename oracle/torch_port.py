@@ -7,7 +7,8 @@ PyTorch's oneDNN/MKL kernels.  This file issues the same ATen ops from a plain s
 checker next to the C oracle and (b) the honest multi-threaded CPU baseline for bench.py
 (`cpu_baseline`, `--impl reference`): the reference tree itself cannot travel to the GPU box.
 Pinned by tests/test_oracle.py against the golden vectors of the unmodified reference.
-Only tests/, smoke() and bench.py's CPU legs may import it.
+Only tests/, smoke() and bench.py's baseline legs (CPU; plus the stock-PyTorch-on-the-same-GPU comparison of
+SURVEY.md 8(d), where the same ATen ops dispatch to cuDNN/cuBLAS) may import it.
 """
 import torch
 import torch.nn.functional as F
@@ -51,7 +52,7 @@ def forward(sd, x, emb, activation="mish"):
     feat = torch.cat((conv_stack(sd, x, activation), emb[:, None, :].expand(B, T, emb.shape[1])), dim=2)
     H = _t(sd, "lstm.weight_hh_l0").shape[1]
     flat = [_t(sd, f"lstm.{n}_l0{s}") for s in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-    zeros = torch.zeros(2, B, H)
+    zeros = torch.zeros(2, B, H, device=feat.device)
     out, _, _ = torch._VF.lstm(feat, (zeros, zeros), flat, True, 1, 0.0, False, True, True)
     y = F.linear(torch.relu(out), _t(sd, "fc1.weight"), _t(sd, "fc1.bias"))
     y = F.linear(torch.relu(y), _t(sd, "fc2.weight"), _t(sd, "fc2.bias"))

@@ -111,3 +111,14 @@ def make_inputs(B, T, dims, seed=1234, normalised_emb=False):
     if normalised_emb:
         emb /= np.linalg.norm(emb, axis=1, keepdims=True)
     return x, emb
+
+
+def loss_inputs(n_fft, B, T, seed):
+    """Seeded inputs of the training-loss chain (tests/golden/make_loss_golden.py): estimate slightly outside [0, 1]
+    (exercises the clamp of torch_spec2wav), target in [0, 1], phase angles in (-pi, pi]; all [B, T, n_fft // 2 + 1]."""
+    F = n_fft // 2 + 1
+    rng = np.random.Generator(np.random.PCG64(seed))
+    est = (rng.random((B, T, F)) * 1.2 - 0.1).astype(np.float32)
+    tgt = rng.random((B, T, F)).astype(np.float32)
+    phase = ((rng.random((B, T, F)) * 2 - 1) * np.pi).astype(np.float32)
+    return est, tgt, phase
