@@ -191,6 +191,37 @@ int vs_wav2spec(vs_engine* e, const float* wav, float* spec, float* phasor, int3
 int vs_spec2wav(vs_engine* e, const float* spec, const float* phasor, float* wav_out, int32_t B, int32_t T,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training-loss chain on the device (BASELINE config 4) -----------------
+ * What train.py:95-109 runs after the mask every step:
+ *   wav = ap.torch_inv_spectrogram(spec, spec_phase)      utils/audio_processor.py:498-509 (torchaudio istft)
+ *   loss = SiSNR_With_Pit()(wav_est, wav_target, seq_len)  utils/generic_utils.py:403-474, C = 1 source
+ * phase_mode VS_ISTFT_Q1 reproduces the reference verbatim (real = mag e^{cos phi}, imag =
+ * mag e^{sin phi}, symmetric Hann); VS_ISTFT_CORRECTED uses mag (cos phi, sin phi) and the periodic Hann of
+ * the analysis side.  All pointers are device pointers; spec / phase are [B][T][F] fp32 (phase = angle in
+ * radians), waveforms [B][hop (T - 1)], seq_len [B] int64 (valid samples, the dataset's wav length).
+ *   vs_loss_spec2wav           spec, phase -> wav                        (the differentiable iSTFT, forward)
+ *   vs_loss_spec2wav_backward  d loss / d wav -> d loss / d spec         (its backward; spec/phase = forward inputs)
+ *   vs_sisnr_loss              est_spec, target_spec, phase, seq_len -> loss (device scalar), optional per-utterance
+ *                              Si-SNR [B] and optional grad_est = d loss / d est_spec [B][T][F]: both iSTFTs, the
+ *                              masked zero-mean Si-SNR, its analytic gradient and the iSTFT backward in one call,
+ *                              no host synchronisation, no Python loop over the batch (generic_utils.py:413-414). */
+enum { VS_ISTFT_Q1 = 0, VS_ISTFT_CORRECTED = 1 };
+typedef struct vs_loss_params {
+    int32_t n_fft, hop_length, win_length;
+    float min_level_db, ref_level_db;
+    int32_t phase_mode;
+} vs_loss_params;
+int vs_loss_configure(vs_engine* e, const vs_loss_params* params, void* stream);
+size_t vs_loss_workspace_bytes(const vs_engine* e, int32_t B, int32_t T);
+int vs_loss_spec2wav(vs_engine* e, const float* spec, const float* phase, float* wav_out, int32_t B, int32_t T,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int vs_loss_spec2wav_backward(vs_engine* e, const float* spec, const float* phase, const float* grad_wav,
+                              float* grad_spec, int32_t B, int32_t T, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int vs_sisnr_loss(vs_engine* e, const float* est_spec, const float* target_spec, const float* phase,
+                  const int64_t* seq_len, float* loss_out, float* snr_out, float* grad_est, int32_t B, int32_t T,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test hooks: run a single conv layer l (0..6 -> 64-channel output) on an fp32 NCHW input
  * in [B][Cin][T][F] -> out [B][64][T][F], and the BiLSTM + head on a given conv_out.
  * They allocate internally and synchronise; not for the hot path. */

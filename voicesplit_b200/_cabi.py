@@ -36,6 +36,11 @@ class VsAudioParams(ctypes.Structure):
                 ("min_level_db", ctypes.c_float), ("ref_level_db", ctypes.c_float)]
 
 
+class VsLossParams(ctypes.Structure):
+    _fields_ = [("n_fft", ctypes.c_int32), ("hop_length", ctypes.c_int32), ("win_length", ctypes.c_int32),
+                ("min_level_db", ctypes.c_float), ("ref_level_db", ctypes.c_float), ("phase_mode", ctypes.c_int32)]
+
+
 class VsTrainState(ctypes.Structure):
     _fields_ = [("running_mean", ctypes.c_void_p * 8), ("running_var", ctypes.c_void_p * 8),
                 ("num_batches_tracked", ctypes.c_void_p * 8), ("momentum", ctypes.c_float)]
@@ -68,6 +73,11 @@ SIGNATURES = {
     "vs_audio_workspace_bytes": (_SZ, [_VP, _I, _I]),
     "vs_wav2spec": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_spec2wav": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_loss_configure": (ctypes.c_int, [_VP, ctypes.POINTER(VsLossParams), _VP]),
+    "vs_loss_workspace_bytes": (_SZ, [_VP, _I, _I]),
+    "vs_loss_spec2wav": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_loss_spec2wav_backward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_sisnr_loss": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),

@@ -36,3 +36,15 @@ class DeviceAudioProcessor:
         return w[0] if single else w
 
     inv_spectrogram = spec2wav
+
+    def configure_training(self, phase_mode="q1"):
+        """Prepare torch_spec2wav / torch_inv_spectrogram (the differentiable iSTFT of the Si-SNR training loss)."""
+        self.engine.configure_loss(self.n_fft, self.hop_length, self.win_length, self.min_level_db, self.ref_level_db, phase_mode)
+
+    def torch_spec2wav(self, spectrogram: torch.Tensor, phase: torch.Tensor):
+        """Reference torch_spec2wav (utils/audio_processor.py:498-509): spectrogram [B, T, F] + phase ANGLE [B, T, F] ->
+        waveform [B, hop (T - 1)], differentiable w.r.t. the spectrogram.  Call configure_training() first."""
+        from .losses import spec2wav_autograd
+        return spec2wav_autograd(self.engine, spectrogram, phase)
+
+    torch_inv_spectrogram = torch_spec2wav

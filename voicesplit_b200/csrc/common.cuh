@@ -118,6 +118,8 @@ struct vs_engine {
     void* pipe = nullptr;
     // STFT / iSTFT state (audio.cu)
     void* audio = nullptr;
+    // differentiable iSTFT + Si-SNR state (loss.cu)
+    void* loss = nullptr;
 
     // tensor-core path state (tc_*.cu)
     void* tc = nullptr;
@@ -154,6 +156,7 @@ void prof_after(vs_engine* e, int id, cudaStream_t st);
 int train_pack(vs_engine* e, const vs_params* p, cudaStream_t st);
 void train_free(vs_engine* e);
 void audio_free(vs_engine* e);
+void loss_free(vs_engine* e);
 
 // fp32 kernels (fp32_kernels.cu); all launch on `st` and return a cudaError_t
 cudaError_t launch_front_fp32(const vs_engine* e, const float* x, float* plane, int B, int T, cudaStream_t st);

@@ -218,6 +218,7 @@ int vs_engine_destroy(vs_engine* e) {
     if (!e) return VS_OK;
     pipe_destroy(e);
     audio_free(e);
+    loss_free(e);
     free_params(e);
     train_free(e);
     tc_destroy(e);

@@ -30,7 +30,7 @@ int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, co
                        int precision, const TcLstmBuffers& lb, cudaStream_t st);
 
 // ---- tc_gemm.cu: the tensor-core GEMM (also used by audio.cu) -----------------------------------
-enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2, GEPI_PLAIN = 3, GEPI_STFT = 4 };
+enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2, GEPI_PLAIN = 3, GEPI_STFT = 4, GEPI_ISTFT_BWD = 5 };
 
 struct GemmTcArgs {
     int M, N, K;
@@ -52,6 +52,11 @@ struct GemmTcArgs {
     float* phasor;
     int rows_per_utt, t_valid, n_bins;
     float min_db, ref_db;
+    // iSTFT-backward epilogue (loss.cu): columns are (dRe, dIm) of a bin; out32 = d loss / d normalised spectrogram
+    // [utt][t_valid][n_bins], chained through the complex build of torch_spec2wav (g_spec = its input, g_phase = angles)
+    const float* g_spec;
+    const float* g_phase;
+    int q1;                     // 1: reference-verbatim exp(cos), exp(sin) weights; 0: cos, sin
 };
 // a.M/N/K, lda, ldw and the epilogue fields must be set; tile shape and pipeline depth are derived here
 int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt16* a_lo, const elt16* w_hi, const elt16* w_lo,

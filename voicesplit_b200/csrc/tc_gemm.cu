@@ -206,6 +206,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                                 }
                             }
                         }
+                    } else if (EPI == GEPI_ISTFT_BWD) {
+                        // utils/audio_processor.py:500-509 backwards: (dRe, dIm) -> d magnitude -> d dB -> d normalised value;
+                        // torch.clamp passes the gradient on the closed interval [0, 1]
+                        const int ub = m / a.rows_per_utt, t = m - ub * a.rows_per_utt;
+                        if (t < a.t_valid) {
+                            const size_t row = ((size_t)ub * a.t_valid + t) * a.n_bins;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const int k = (nbase + j) >> 1;
+                                if (k < a.n_bins && c0 + j < a.n_tile) {
+                                    const float sv = a.g_spec[row + k];
+                                    float g = 0.f;
+                                    if (sv >= 0.f && sv <= 1.f) {
+                                        float sn, cs;
+                                        sincosf(a.g_phase[row + k], &sn, &cs);
+                                        const float wr = a.q1 ? expf(cs) : cs, wi = a.q1 ? expf(sn) : sn;
+                                        const float amp = exp10f(((sv - 1.f) * -a.min_db + a.ref_db) * 0.05f);
+                                        g = (acc[i][j] * wr + acc[i][j + 1] * wi) * amp * (0.05f * 2.302585093f * -a.min_db);
+                                    }
+                                    a.out32[row + k] = g;
+                                }
+                            }
+                        }
                     } else if (EPI == GEPI_FC1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -404,6 +427,7 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     } while (0)
     if (epi == GEPI_PLAIN) { if (elt) VS_GEMM_TC(GEPI_PLAIN, 1); else VS_GEMM_TC(GEPI_PLAIN, 0); }
     else if (epi == GEPI_STFT) { if (elt) VS_GEMM_TC(GEPI_STFT, 1); else VS_GEMM_TC(GEPI_STFT, 0); }
+    else if (epi == GEPI_ISTFT_BWD) { if (elt) VS_GEMM_TC(GEPI_ISTFT_BWD, 1); else VS_GEMM_TC(GEPI_ISTFT_BWD, 0); }
     else if (epi == GEPI_GATES) { if (elt) VS_GEMM_TC(GEPI_GATES, 1); else VS_GEMM_TC(GEPI_GATES, 0); }
     else if (epi == GEPI_FC1) { if (elt) VS_GEMM_TC(GEPI_FC1, 1); else VS_GEMM_TC(GEPI_FC1, 0); }
     else { if (elt) VS_GEMM_TC(GEPI_FC2, 1); else VS_GEMM_TC(GEPI_FC2, 0); }

@@ -190,6 +190,69 @@ class MaskEngine:
         _, masked = self.forward(spec, emb, precision=precision, want_masked=True)
         return self.spec2wav(masked, phasor)
 
+    # ---- training-loss chain: differentiable iSTFT (train.py:99-100) + Si-SNR (train.py:108) ------------------
+    PHASE_MODES = {"q1": 0, "corrected": 1}
+
+    def configure_loss(self, n_fft=1200, hop_length=160, win_length=400, min_level_db=-100.0, ref_level_db=20.0, phase_mode="q1"):
+        """phase_mode "q1" = the reference verbatim, "corrected" = mag (cos, sin) + periodic Hann."""
+        if phase_mode not in self.PHASE_MODES:
+            raise ValueError(f"phase_mode must be one of {sorted(self.PHASE_MODES)}")
+        p = _cabi.VsLossParams(n_fft, hop_length, win_length, min_level_db, ref_level_db, self.PHASE_MODES[phase_mode])
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_loss_configure(self.handle, ctypes.byref(p), ctypes.c_void_p(st)), "vs_loss_configure")
+        self.loss_cfg = dict(n_fft=n_fft, hop_length=hop_length, win_length=win_length, phase_mode=phase_mode)
+
+    def _loss_ws(self, B, T, device):
+        need = int(self.lib.vs_loss_workspace_bytes(self.handle, B, T))
+        if need == 0:
+            raise RuntimeError("call configure_loss first (and use T >= 2 frames)")
+        return torch.empty(need, dtype=torch.uint8, device=device), need
+
+    @staticmethod
+    def _f32c(t):
+        return t.detach().to(torch.float32).contiguous()
+
+    def loss_spec2wav(self, spec, phase):
+        """spec, phase (angle) [B, T, F] -> wav [B, hop (T - 1)]   (torch_spec2wav, audio_processor.py:498-509)"""
+        spec, phase = self._f32c(spec), self._f32c(phase)
+        B, T, _ = spec.shape
+        with torch.cuda.device(spec.device):
+            ws, need = self._loss_ws(B, T, spec.device)
+            wav = torch.empty(B, self.loss_cfg["hop_length"] * (T - 1), dtype=torch.float32, device=spec.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_loss_spec2wav(self.handle, _ptr(spec), _ptr(phase), _ptr(wav), B, T, _ptr(ws), need, ctypes.c_void_p(st)),
+                        "vs_loss_spec2wav")
+        return wav
+
+    def loss_spec2wav_backward(self, spec, phase, grad_wav):
+        spec, phase, grad_wav = self._f32c(spec), self._f32c(phase), self._f32c(grad_wav)
+        B, T, _ = spec.shape
+        with torch.cuda.device(spec.device):
+            ws, need = self._loss_ws(B, T, spec.device)
+            grad = torch.empty_like(spec)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_loss_spec2wav_backward(self.handle, _ptr(spec), _ptr(phase), _ptr(grad_wav), _ptr(grad), B, T, _ptr(ws), need,
+                                                           ctypes.c_void_p(st)), "vs_loss_spec2wav_backward")
+        return grad
+
+    def sisnr_loss(self, est_spec, target_spec, phase, seq_len, want_grad=True):
+        """-> (loss [] , snr [B], grad_est [B, T, F] or None): train.py:95-108 in one call, no host synchronisation."""
+        est, tgt, phase = self._f32c(est_spec), self._f32c(target_spec), self._f32c(phase)
+        B, T, _ = est.shape
+        lens = seq_len.detach().reshape(-1).to(device=est.device, dtype=torch.int64).contiguous()
+        if lens.numel() != B:
+            raise ValueError("seq_len must hold one length per utterance")
+        with torch.cuda.device(est.device):
+            ws, need = self._loss_ws(B, T, est.device)
+            loss = torch.empty((), dtype=torch.float32, device=est.device)
+            snr = torch.empty(B, dtype=torch.float32, device=est.device)
+            grad = torch.empty_like(est) if want_grad else None
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_sisnr_loss(self.handle, _ptr(est), _ptr(tgt), _ptr(phase), _ptr(lens), _ptr(loss), _ptr(snr),
+                                               _ptr(grad) if want_grad else None, B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_sisnr_loss")
+        return loss, snr, grad
+
     # ---- training (fp32, batch-statistics BatchNorm, full backward) ------------------------------
     PARAM_ORDER = tuple([k for l in range(8) for k in (f"conv.{CONV_IDX[l]}.weight", f"conv.{CONV_IDX[l]}.bias",
                                                         f"conv.{BN_IDX[l]}.weight", f"conv.{BN_IDX[l]}.bias")] +
