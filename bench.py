@@ -344,7 +344,7 @@ def main():
 def extra_measurements(dev):
     from voicesplit_b200 import config as vconfig
     from voicesplit_b200.engine import MaskEngine
-    from voicesplit_b200.losses import si_snr_with_pit
+    from voicesplit_b200.losses import SpecSiSNRLoss
     from models.voicesplit.model import VoiceSplit
     out = {}
     dims = synth.make_dims(601, 256, 400, 600)
@@ -359,7 +359,8 @@ def extra_measurements(dev):
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
-    # ---- config 4: forward (batch-stat BatchNorm) + Si-SNR-PIT + backward + Adam, B = 8, 301 x 601
+    # ---- config 4: forward (batch-stat BatchNorm) + loss chain of train.py:95-108 (both spectrograms through the Q1-faithful
+    # differentiable iSTFT, then Si-SNR) + backward + Adam, B = 8, 301 x 601
     model = VoiceSplit(vconfig.AttrDict(synth.make_config_dict(dims)))
     model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()})
     model = model.to(dev).train()
@@ -368,16 +369,20 @@ def extra_measurements(dev):
     x, emb = synth.make_inputs(B, T, dims, 7)
     x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
     target = torch.rand(B, T, F, device=dev) * x
-    lengths = torch.full((B,), T * F, device=dev)
+    phase = (torch.rand(B, T, F, device=dev) * 2 - 1) * np.pi
+    seq_len = torch.full((B, 1), 160 * (T - 1), device=dev, dtype=torch.int64)
+    crit = SpecSiSNRLoss(model.engine(dev), dict(n_fft=1200, hop_length=160, win_length=400), "q1")
 
     def step():
         opt.zero_grad(set_to_none=True)
         mask = model(x, emb)
-        si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths).backward()
+        crit(mask * x, target, phase, seq_len).backward()
         opt.step()
-    ms = timed(step, 3)
+    step(); step()
+    ms = timed(step, 8)
     out["train_step_config4"] = {"value": B / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "per_gpu_batch": B, "frames": T, "freq_bins": F,
-                                 "what": "forward (batch-stat BN) + Si-SNR-PIT + backward + Adam; conv fwd/dgrad/wgrad on tcgen05 (fp16x3/bf16x3), rest fp32"}
+                                 "what": "forward (batch-stat BN) + differentiable iSTFT x2 + Si-SNR (one fused engine call) + backward + Adam; "
+                                         "conv fwd/dgrad/wgrad, LSTM input GEMMs and the iSTFT GEMMs on tcgen05 (fp16x3/bf16x3), rest fp32"}
     del model, opt
     torch.cuda.empty_cache()
     # ---- config 5: 3 s @ 16 kHz waveform -> STFT -> mask -> iSTFT -> waveform, B = 64

@@ -1,5 +1,7 @@
-"""Training-step benchmark (BASELINE config 4 shape): forward (batch-stat BatchNorm) + Si-SNR-PIT loss +
-backward + ONE flat NCCL gradient all-reduce + Adam step, data-parallel over the ranks it is launched on.
+"""Training-step benchmark (BASELINE config 4 shape): forward (batch-stat BatchNorm) + the reference's loss chain
+(both spectrograms through the differentiable iSTFT, then Si-SNR: train.py:95-108, one engine call) + backward + ONE
+flat NCCL gradient all-reduce + Adam step, data-parallel over the ranks it is launched on.  --loss flat applies the
+general-C torch criterion to the flattened spectrograms instead (no iSTFT), the round-1 early variant.
 
     python tools/train_bench.py --batch 8 --steps 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_bench.py --batch 8
@@ -18,7 +20,22 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from voicesplit_b200 import config, dist as vdist, synth  # noqa: E402
-from voicesplit_b200.losses import si_snr_with_pit  # noqa: E402
+from voicesplit_b200.losses import SpecSiSNRLoss, si_snr_with_pit  # noqa: E402
+
+
+def eager_loss_chain(est, tgt, phase, lens, n_fft=1200, hop=160, win=400, min_db=-100.0, ref_db=20.0):
+    """The reference's loss chain as stock torch ops on the GPU (torch_spec2wav with torch.istft standing in for the removed
+    torchaudio.functional.istft, then the C = 1 criterion) - the eager baseline the fused engine call is timed against."""
+    window = torch.hann_window(win, periodic=False, device=est.device)
+
+    def spec2wav(spec):
+        S = (torch.clamp(spec, 0.0, 1.0) - 1.0) * -min_db + ref_db
+        mag = torch.pow(10.0, S * 0.05).transpose(2, 1)
+        ph = phase.transpose(2, 1)
+        z = torch.complex(mag * torch.exp(ph.cos()), mag * torch.exp(ph.sin()))
+        return torch.istft(z, n_fft, hop_length=hop, win_length=win, window=window, center=True)
+    B = est.shape[0]
+    return si_snr_with_pit(spec2wav(est).view(B, 1, -1), spec2wav(tgt).view(B, 1, -1), lens.view(-1))
 
 
 def main():
@@ -26,8 +43,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=301)
     ap.add_argument("--freq", type=int, default=601)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--loss", choices=("istft", "flat"), default="istft")
     ap.add_argument("--cpu-reference", action="store_true", help="also time PyTorch autograd on the host CPU (B=2)")
     args = ap.parse_args()
     rank, world, local = vdist.env_rank()
@@ -45,6 +63,14 @@ def main():
     x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
     target = torch.rand(B, T, F, device=dev) * x
     lengths = torch.full((B,), T * F, device=dev)
+    phase = (torch.rand(B, T, F, device=dev) * 2 - 1) * np.pi
+    seq_len = torch.full((B, 1), 160 * (T - 1), device=dev, dtype=torch.int64)
+    crit = SpecSiSNRLoss(model.engine(dev), dict(n_fft=2 * (F - 1), hop_length=160, win_length=400)) if args.loss == "istft" else None
+
+    def criterion(mask):
+        if crit is not None:
+            return crit(mask * x, target, phase, seq_len)
+        return si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths)
 
     sections = {}
 
@@ -58,7 +84,7 @@ def main():
         opt.zero_grad(set_to_none=True)
         mask = model(x, emb)
         t1 = mark()
-        loss = si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths)
+        loss = criterion(mask)
         loss.backward()
         t2 = mark()
         n = vdist.allreduce_gradients(model.parameters(), dist)
@@ -79,7 +105,7 @@ def main():
     opt.zero_grad(set_to_none=True)
     mask = model(x, emb)
     fwd = eng.profile_read()
-    si_snr_with_pit((mask * x).view(B, 1, -1), target.view(B, 1, -1), lengths).backward()
+    criterion(mask).backward()
     bwd = eng.profile_read()
     eng.set_profiling(False)
     breakdown = {}
@@ -102,7 +128,28 @@ def main():
     for _ in range(2):
         step(timed=True)
     if rank == 0:
-        out = {"metric": "training utterances/s (forward + Si-SNR-PIT + backward + grad all-reduce + Adam)", "value": thr,
+        chain = None
+        if crit is not None:       # the loss chain alone: fused engine call vs the same chain as stock torch ops on this GPU
+            est = (mask.detach() * x).requires_grad_(True)
+
+            def t_ms(fn, n=5):
+                fn(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record(); torch.cuda.synchronize()
+                return a.elapsed_time(b) / n
+            fused = t_ms(lambda: crit(est, target, phase, seq_len).backward())
+            eager = t_ms(lambda: eager_loss_chain(est, target, phase, seq_len).backward())
+            est.grad = None
+            l_f = crit(est, target, phase, seq_len); l_f.backward(); g_f = est.grad.clone(); est.grad = None
+            l_e = eager_loss_chain(est, target, phase, seq_len); l_e.backward()
+            chain = {"fused_ms": round(fused, 3), "eager_torch_ms": round(eager, 3), "loss_fused": float(l_f.detach()), "loss_eager": float(l_e.detach()),
+                     "grad_max_rel_diff": float((g_f - est.grad).abs().max() / est.grad.abs().max())}
+        out = {"metric": "training utterances/s (forward + iSTFT/Si-SNR loss chain + backward + grad all-reduce + Adam)"
+               if crit is not None else "training utterances/s (forward + Si-SNR-PIT + backward + grad all-reduce + Adam)", "value": thr,
+               "loss": args.loss, "loss_chain": chain,
                "n_gpus": world, "per_gpu_batch": B, "frames": T, "freq_bins": F, "ms_per_step": ms / args.steps,
                "allreduce_floats": nred, "losses": losses, "arithmetic": "fp32 CUDA cores (training path)",
                "bn_statistics": "per rank", "kernel_ms": breakdown,

@@ -123,6 +123,16 @@ class MaskEstimator(nn.Module):
             self._packed_sig = sig
         return self._engine
 
+    def engine(self, device=None):
+        """The MaskEngine behind this module on `device` (default: where the parameters live), parameters packed and current.
+        Other engine services - the audio front end, the loss chain (losses.SpecSiSNRLoss) - attach to it."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("voicesplit_b200 runs on sm_100a CUDA devices only: move the module with .cuda() first")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return self._sync_engine(device)
+
     def _guard(self, x):
         if not x.is_cuda:
             raise RuntimeError("voicesplit_b200 runs on sm_100a CUDA devices only: move the module and inputs "
