@@ -360,12 +360,12 @@ def extra_measurements(dev):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
     # ---- config 4: forward (batch-stat BatchNorm) + loss chain of train.py:95-108 (both spectrograms through the Q1-faithful
-    # differentiable iSTFT, then Si-SNR) + backward + Adam, B = 8, 301 x 601
+    # differentiable iSTFT, then Si-SNR) + backward + Adam, B = 32, 301 x 601
     model = VoiceSplit(vconfig.AttrDict(synth.make_config_dict(dims)))
     model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()})
     model = model.to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    B, T, F = 8, 301, 601
+    B, T, F = 32, 301, 601
     x, emb = synth.make_inputs(B, T, dims, 7)
     x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
     target = torch.rand(B, T, F, device=dev) * x
@@ -379,7 +379,7 @@ def extra_measurements(dev):
         crit(mask * x, target, phase, seq_len).backward()
         opt.step()
     step(); step()
-    ms = timed(step, 8)
+    ms = timed(step, 6)
     out["train_step_config4"] = {"value": B / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "per_gpu_batch": B, "frames": T, "freq_bins": F,
                                  "what": "forward (batch-stat BN) + differentiable iSTFT x2 + Si-SNR (one fused engine call) + backward + Adam; "
                                          "conv fwd/dgrad/wgrad, LSTM input GEMMs and the iSTFT GEMMs on tcgen05 (fp16x3/bf16x3), rest fp32"}
