@@ -122,3 +122,41 @@ def loss_inputs(n_fft, B, T, seed):
     tgt = rng.random((B, T, F)).astype(np.float32)
     phase = ((rng.random((B, T, F)) * 2 - 1) * np.pi).astype(np.float32)
     return est, tgt, phase
+
+
+def make_encoder_state_dict(seed, flavour="default", num_mels=40, hidden=768, layers=3, emb_dim=256):
+    """GE2E speaker-encoder parameters under the notebook's state_dict keys (lstm.*_l{0..2}, proj.linear_layer.*).
+    "default": PyTorch's U(-1/sqrt(H), 1/sqrt(H)); "stress": 3x larger weights and biases (still non-chaotic), so that
+    gate saturation and error accumulation over 80 steps x 3 layers are exercised."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k = 1.0 / np.sqrt(hidden)
+    s = 3.0 if flavour == "stress" else 1.0
+    sd = {}
+    for l in range(layers):
+        d_in = num_mels if l == 0 else hidden
+        sd[f"lstm.weight_ih_l{l}"] = (rng.uniform(-k, k, (4 * hidden, d_in)) * s).astype(np.float32)
+        sd[f"lstm.weight_hh_l{l}"] = (rng.uniform(-k, k, (4 * hidden, hidden)) * s).astype(np.float32)
+        sd[f"lstm.bias_ih_l{l}"] = (rng.uniform(-k, k, 4 * hidden) * s).astype(np.float32)
+        sd[f"lstm.bias_hh_l{l}"] = (rng.uniform(-k, k, 4 * hidden) * s).astype(np.float32)
+    sd["proj.linear_layer.weight"] = (rng.uniform(-k, k, (emb_dim, hidden)) * s).astype(np.float32)
+    sd["proj.linear_layer.bias"] = (rng.uniform(-k, k, emb_dim) * s).astype(np.float32)
+    return sd
+
+
+def make_reference_audio(B, L, seed):
+    """Speech-like test signals [B, L] at 16 kHz: a few harmonics with slow amplitude modulation plus noise."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.arange(L) / 16000.0
+    out = np.zeros((B, L))
+    for b in range(B):
+        f0 = rng.uniform(90, 250)
+        for h in range(1, 9):
+            out[b] += rng.uniform(0.2, 1.0) / h * np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6.28)) * (0.6 + 0.4 * np.sin(2 * np.pi * rng.uniform(1, 4) * t))
+        out[b] = 0.05 * out[b] / np.abs(out[b]).max() + 0.002 * rng.standard_normal(L)
+    return out.astype(np.float32)
+
+
+def encoder_mel_inputs(seed, frames, num_mels=40):
+    """log-mel-like encoder inputs, one [num_mels, T] array per entry of `frames` (values in get_mel's range, about -6 .. 1)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return [(rng.standard_normal((num_mels, T)) * 1.2 - 2.5).astype(np.float32) for T in frames]
