@@ -222,6 +222,38 @@ int vs_sisnr_loss(vs_engine* e, const float* est_spec, const float* target_spec,
                   const int64_t* seq_len, float* loss_out, float* snr_out, float* grad_est, int32_t B, int32_t T,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- GE2E speaker encoder: the producer of the d-vector ---------------------
+ * Replaces, for the extraction loop of notebooks/GE2E-Seungwonpark-ExtractSpeakerEmbedding-adaptado-para-openvoicefilter.py
+ * (:141-143):  mel = ap.get_mel(wav)   (utils/audio_processor.py:456-468: |librosa.stft|^2 -> mel basis -> log10(. + 1e-6))
+ *              dvec = embedder(mel)    (SpeakerEncoder.forward, notebook :75-85: windows of `window` frames every `stride`,
+ *                                       `lstm_layers` x LSTM(lstm_hidden), last frame, Linear -> emb_dim, L2 normalise, mean)
+ * The mel front end shares the STFT of vs_audio_configure (call that first; n_fft / hop / win come from it).
+ * Device layouts: wav [B][L] fp32; mel [B][T][num_mels] fp32 (frames are rows: the transpose of the reference's
+ * [num_mels, T]); dvec [B][emb_dim] fp32.  All utterances of a call have the same length; T = 1 + L / hop >= window.
+ * Parameters are PyTorch nn.LSTM / nn.Linear tensors (gate order i, f, g, o), device pointers, per layer. */
+typedef struct vs_encoder_dims {
+    int32_t num_mels, lstm_layers, lstm_hidden, emb_dim, window, stride; /* notebook :34-41: 40, 3, 768, 256, 80, 40 */
+    int32_t sample_rate;                                                  /* 16000 */
+} vs_encoder_dims;
+typedef struct vs_encoder_params {
+    const float* w_ih[4]; /* lstm.weight_ih_l{k} [4H][num_mels | H] */
+    const float* w_hh[4]; /* lstm.weight_hh_l{k} [4H][H] */
+    const float* b_ih[4]; /* lstm.bias_ih_l{k} [4H] */
+    const float* b_hh[4]; /* lstm.bias_hh_l{k} [4H] */
+    const float* proj_w;  /* proj.linear_layer.weight [emb_dim][H] */
+    const float* proj_b;  /* proj.linear_layer.bias [emb_dim] */
+} vs_encoder_params;
+int vs_encoder_configure(vs_engine* e, const vs_encoder_dims* dims, void* stream);
+int vs_encoder_load_params(vs_engine* e, const vs_encoder_params* params, void* stream);
+/* from_wav != 0: `n` is the waveform length L (vs_encoder_mel / vs_encoder_dvector); else the frame count T (vs_encoder_forward) */
+size_t vs_encoder_workspace_bytes(const vs_engine* e, int32_t B, int32_t n, int32_t from_wav);
+int vs_encoder_mel(vs_engine* e, const float* wav, float* mel_out, int32_t B, int32_t L, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int vs_encoder_forward(vs_engine* e, const float* mel, float* dvec, int32_t B, int32_t T, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int vs_encoder_dvector(vs_engine* e, const float* wav, float* dvec, int32_t B, int32_t L, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Test hooks: run a single conv layer l (0..6 -> 64-channel output) on an fp32 NCHW input
  * in [B][Cin][T][F] -> out [B][64][T][F], and the BiLSTM + head on a given conv_out.
  * They allocate internally and synchronise; not for the hot path. */

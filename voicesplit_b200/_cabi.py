@@ -41,6 +41,15 @@ class VsLossParams(ctypes.Structure):
                 ("min_level_db", ctypes.c_float), ("ref_level_db", ctypes.c_float), ("phase_mode", ctypes.c_int32)]
 
 
+class VsEncoderDims(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("num_mels", "lstm_layers", "lstm_hidden", "emb_dim", "window", "stride", "sample_rate")]
+
+
+class VsEncoderParams(ctypes.Structure):
+    _fields_ = [("w_ih", ctypes.c_void_p * 4), ("w_hh", ctypes.c_void_p * 4), ("b_ih", ctypes.c_void_p * 4), ("b_hh", ctypes.c_void_p * 4),
+                ("proj_w", ctypes.c_void_p), ("proj_b", ctypes.c_void_p)]
+
+
 class VsTrainState(ctypes.Structure):
     _fields_ = [("running_mean", ctypes.c_void_p * 8), ("running_var", ctypes.c_void_p * 8),
                 ("num_batches_tracked", ctypes.c_void_p * 8), ("momentum", ctypes.c_float)]
@@ -78,6 +87,12 @@ SIGNATURES = {
     "vs_loss_spec2wav": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_loss_spec2wav_backward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_sisnr_loss": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_encoder_configure": (ctypes.c_int, [_VP, ctypes.POINTER(VsEncoderDims), _VP]),
+    "vs_encoder_load_params": (ctypes.c_int, [_VP, ctypes.POINTER(VsEncoderParams), _VP]),
+    "vs_encoder_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "vs_encoder_mel": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_encoder_forward": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_encoder_dvector": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),

@@ -129,6 +129,36 @@ static AudioWs audio_carve(const AudioState* s, int B, int L, int T, void* base)
     return w;
 }
 
+// |STFT|^2 of wav [B][L] as bf16 hi/lo planes [B * T][ld16] (T = 1 + L / hop), for the mel front end of encoder.cu
+size_t audio_stft_scratch_bytes(const vs_engine* e, int B, int L) {
+    if (!e->audio) return 0;
+    const AudioState* s = (const AudioState*)e->audio;
+    const size_t Lp = (size_t)((L + s->n_fft + s->hop - 1) / s->hop) * s->hop;
+    return 2 * align_up((size_t)B * Lp * 2 + 4096, 1024);
+}
+int audio_stft_power(vs_engine* e, const float* wav, elt16* pw_hi, elt16* pw_lo, int ld16, int B, int L, void* scratch, cudaStream_t st) {
+    if (!e->audio) { set_error("call vs_audio_configure first"); return VS_ERR_STATE; }
+    const AudioState* s = (const AudioState*)e->audio;
+    if (L <= s->n_fft / 2) { set_error("signal shorter than n_fft / 2 cannot be reflect-padded"); return VS_ERR_INVALID; }
+    const int Tp = (L + s->n_fft + s->hop - 1) / s->hop, Lp = Tp * s->hop, T = 1 + L / s->hop;
+    elt16* y_hi = (elt16*)scratch;
+    elt16* y_lo = (elt16*)((char*)scratch + align_up((size_t)B * Lp * 2 + 4096, 1024));
+    {
+        const long long n = (long long)B * Lp;
+        k_wav_prep<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wav, y_hi, y_lo, L, Lp, s->n_fft / 2, n);
+        VS_LAUNCH(e, KID_CONVERT, st, cudaGetLastError());
+    }
+    GemmTcArgs a{};
+    a.M = B * Tp; a.N = 2 * s->bins; a.K = s->win; a.lda = s->hop; a.ldw = s->win;
+    a.out_hi = pw_hi; a.out_lo = pw_lo; a.ld16 = ld16; a.rows_per_utt = Tp; a.t_valid = T; a.n_bins = s->bins;
+    const int lp = (s->n_fft - s->win) / 2;
+    return launch_gemm_tc(e, GEPI_STFT_POWER, KID_HEAD, y_hi + lp, y_lo + lp, s->dft_hi, s->dft_lo, a, VS_PREC_FP16X3, st);
+}
+void audio_geometry(const vs_engine* e, int* n_fft, int* hop, int* win) {
+    const AudioState* s = (const AudioState*)e->audio;
+    *n_fft = s ? s->n_fft : 0; *hop = s ? s->hop : 0; *win = s ? s->win : 0;
+}
+
 }  // namespace vs
 
 using namespace vs;

@@ -120,6 +120,8 @@ struct vs_engine {
     void* audio = nullptr;
     // differentiable iSTFT + Si-SNR state (loss.cu)
     void* loss = nullptr;
+    // GE2E speaker encoder (encoder.cu)
+    void* encoder = nullptr;
 
     // tensor-core path state (tc_*.cu)
     void* tc = nullptr;
@@ -157,6 +159,7 @@ int train_pack(vs_engine* e, const vs_params* p, cudaStream_t st);
 void train_free(vs_engine* e);
 void audio_free(vs_engine* e);
 void loss_free(vs_engine* e);
+void encoder_free(vs_engine* e);
 
 // fp32 kernels (fp32_kernels.cu); all launch on `st` and return a cudaError_t
 cudaError_t launch_front_fp32(const vs_engine* e, const float* x, float* plane, int B, int T, cudaStream_t st);

@@ -219,6 +219,7 @@ int vs_engine_destroy(vs_engine* e) {
     pipe_destroy(e);
     audio_free(e);
     loss_free(e);
+    encoder_free(e);
     free_params(e);
     train_free(e);
     tc_destroy(e);

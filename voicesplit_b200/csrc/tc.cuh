@@ -29,8 +29,20 @@ int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_i
 int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, const float* x, float* mask, int B, int T,
                        int precision, const TcLstmBuffers& lb, cudaStream_t st);
 
+// gate nonlinearities of the recurrent kernels (tc_lstm.cu, encoder.cu)
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    // 1 / (1 + 2^(-x log2 e)) with the raw MUFU approximations (no range/denormal slow paths):
+    // ex2.approx and rcp.approx are each accurate to ~2^-22 relative
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
+
+
 // ---- tc_gemm.cu: the tensor-core GEMM (also used by audio.cu) -----------------------------------
-enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2, GEPI_PLAIN = 3, GEPI_STFT = 4, GEPI_ISTFT_BWD = 5 };
+enum { GEPI_GATES = 0, GEPI_FC1 = 1, GEPI_FC2 = 2, GEPI_PLAIN = 3, GEPI_STFT = 4, GEPI_ISTFT_BWD = 5, GEPI_STFT_POWER = 6, GEPI_LOGMEL = 7 };
 
 struct GemmTcArgs {
     int M, N, K;
@@ -57,12 +69,19 @@ struct GemmTcArgs {
     const float* g_spec;
     const float* g_phase;
     int q1;                     // 1: reference-verbatim exp(cos), exp(sin) weights; 0: cos, sin
+    // encoder.cu: STFT_POWER writes |D|^2 of bin k as bf16 hi/lo into out_hi/out_lo [utt * t_valid + t][ld16];
+    //             LOGMEL writes log10(acc + 1e-6) as fp32 (out32, optional) and fp16 hi/lo (out_hi/out_lo, [M][ld16])
 };
 // a.M/N/K, lda, ldw and the epilogue fields must be set; tile shape and pipeline depth are derived here
 int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt16* a_lo, const elt16* w_hi, const elt16* w_lo,
                    GemmTcArgs a, int precision, cudaStream_t st);
 
 
+
+// audio.cu services used by encoder.cu
+size_t audio_stft_scratch_bytes(const vs_engine* e, int B, int L);
+int audio_stft_power(vs_engine* e, const float* wav, elt16* pw_hi, elt16* pw_lo, int ld16, int B, int L, void* scratch, cudaStream_t st);
+void audio_geometry(const vs_engine* e, int* n_fft, int* hop, int* win);
 
 // training GEMMs on the tensor-core kernel (tc_gemm.cu)
 size_t tc_train_gemm_workspace_bytes(const vs_engine* e, int B, int T);

@@ -206,6 +206,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                                 }
                             }
                         }
+                    } else if (EPI == GEPI_STFT_POWER) {
+                        const int ub = m / a.rows_per_utt, t = m - ub * a.rows_per_utt;
+                        if (t < a.t_valid) {
+                            const size_t row = ((size_t)ub * a.t_valid + t) * a.ld16;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const int k = (nbase + j) >> 1;
+                                if (k < a.n_bins && c0 + j < a.n_tile) {
+                                    const float re = acc[i][j], im = acc[i][j + 1];
+                                    elt16 vh, vl;
+                                    split16<0>(fmaf(re, re, im * im), vh, vl);      // bf16: the power spans many decades
+                                    a.out_hi[row + k] = vh;
+                                    a.out_lo[row + k] = vl;
+                                }
+                            }
+                        }
+                    } else if (EPI == GEPI_LOGMEL) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nbase + j;
+                            if (n < a.N && c0 + j < a.n_tile) {
+                                const float v = log10f(acc[i][j] + 1e-6f);         // utils/audio_processor.py:467
+                                if (a.out32) a.out32[(size_t)m * a.ld_out + n] = v;
+                                elt16 vh, vl;
+                                split16<1>(v, vh, vl);
+                                a.out_hi[(size_t)m * a.ld16 + n] = vh;
+                                a.out_lo[(size_t)m * a.ld16 + n] = vl;
+                            }
+                        }
                     } else if (EPI == GEPI_ISTFT_BWD) {
                         // utils/audio_processor.py:500-509 backwards: (dRe, dIm) -> d magnitude -> d dB -> d normalised value;
                         // torch.clamp passes the gradient on the closed interval [0, 1]
@@ -428,6 +457,8 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     if (epi == GEPI_PLAIN) { if (elt) VS_GEMM_TC(GEPI_PLAIN, 1); else VS_GEMM_TC(GEPI_PLAIN, 0); }
     else if (epi == GEPI_STFT) { if (elt) VS_GEMM_TC(GEPI_STFT, 1); else VS_GEMM_TC(GEPI_STFT, 0); }
     else if (epi == GEPI_ISTFT_BWD) { if (elt) VS_GEMM_TC(GEPI_ISTFT_BWD, 1); else VS_GEMM_TC(GEPI_ISTFT_BWD, 0); }
+    else if (epi == GEPI_STFT_POWER) { if (elt) VS_GEMM_TC(GEPI_STFT_POWER, 1); else VS_GEMM_TC(GEPI_STFT_POWER, 0); }
+    else if (epi == GEPI_LOGMEL) { if (elt) VS_GEMM_TC(GEPI_LOGMEL, 1); else VS_GEMM_TC(GEPI_LOGMEL, 0); }
     else if (epi == GEPI_GATES) { if (elt) VS_GEMM_TC(GEPI_GATES, 1); else VS_GEMM_TC(GEPI_GATES, 0); }
     else if (epi == GEPI_FC1) { if (elt) VS_GEMM_TC(GEPI_FC1, 1); else VS_GEMM_TC(GEPI_FC1, 0); }
     else { if (elt) VS_GEMM_TC(GEPI_FC2, 1); else VS_GEMM_TC(GEPI_FC2, 0); }

@@ -40,16 +40,6 @@ struct LstmTcArgs {
 // timing[4] cell thread 64: waiting for acc_full    timing[5] cell thread 64: TMEM load + gate math
 // timing[6] cell thread 64: stores                  timing[7] cell thread 64: bar.sync + fence + atomic
 
-__device__ __forceinline__ float sigmoid_fast(float x) {
-    // 1 / (1 + 2^(-x log2 e)) with the raw MUFU approximations (no range/denormal slow paths):
-    // ex2.approx and rcp.approx are each accurate to ~2^-22 relative
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
-    return r;
-}
-__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
-
 template <int ELT>
 __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __grid_constant__ CUtensorMap tm_w_hi,
                                                     const __grid_constant__ CUtensorMap tm_w_lo,

@@ -253,6 +253,82 @@ class MaskEngine:
                                                _ptr(grad) if want_grad else None, B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_sisnr_loss")
         return loss, snr, grad
 
+    # ---- GE2E speaker encoder: wav -> log-mel -> 3 x LSTM -> d-vector (notebooks/GE2E-...-openvoicefilter.py:63-85,141-143) ----
+    def configure_encoder(self, num_mels=40, lstm_layers=3, lstm_hidden=768, emb_dim=256, window=80, stride=40, sample_rate=16000):
+        """Needs configure_audio() first: the mel front end shares its STFT (n_fft / hop / win)."""
+        if getattr(self, "audio", None) is None:
+            raise RuntimeError("call configure_audio() before configure_encoder()")
+        d = _cabi.VsEncoderDims(num_mels, lstm_layers, lstm_hidden, emb_dim, window, stride, sample_rate)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_encoder_configure(self.handle, ctypes.byref(d), ctypes.c_void_p(st)), "vs_encoder_configure")
+        self.encoder_cfg = dict(num_mels=num_mels, lstm_layers=lstm_layers, lstm_hidden=lstm_hidden, emb_dim=emb_dim, window=window, stride=stride)
+
+    def load_encoder_state_dict(self, sd):
+        """sd: the notebook's SpeakerEncoder state_dict (lstm.weight_ih_l{k}, ..., proj.linear_layer.weight/bias), CUDA fp32 tensors."""
+        c = self.encoder_cfg
+        keep = []
+
+        def g(k):
+            t = sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        p = _cabi.VsEncoderParams()
+        for l in range(c["lstm_layers"]):
+            p.w_ih[l], p.w_hh[l] = g(f"lstm.weight_ih_l{l}"), g(f"lstm.weight_hh_l{l}")
+            p.b_ih[l], p.b_hh[l] = g(f"lstm.bias_ih_l{l}"), g(f"lstm.bias_hh_l{l}")
+        p.proj_w, p.proj_b = g("proj.linear_layer.weight"), g("proj.linear_layer.bias")
+        H, M = c["lstm_hidden"], c["num_mels"]
+        for l in range(c["lstm_layers"]):
+            if tuple(sd[f"lstm.weight_ih_l{l}"].shape) != (4 * H, M if l == 0 else H) or tuple(sd[f"lstm.weight_hh_l{l}"].shape) != (4 * H, H):
+                raise ValueError(f"encoder layer {l}: parameter shapes do not match the configured dimensions")
+        if tuple(sd["proj.linear_layer.weight"].shape) != (c["emb_dim"], H):
+            raise ValueError("encoder projection shape does not match the configured dimensions")
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_encoder_load_params(self.handle, ctypes.byref(p), ctypes.c_void_p(st)), "vs_encoder_load_params")
+            torch.cuda.current_stream().synchronize()      # the packing kernels read `keep`
+
+    def _enc_ws(self, B, n, from_wav, device):
+        need = int(self.lib.vs_encoder_workspace_bytes(self.handle, B, n, 1 if from_wav else 0))
+        if need == 0:
+            raise RuntimeError("call configure_encoder first")
+        return torch.empty(need, dtype=torch.uint8, device=device), need
+
+    def encoder_mel(self, wav):
+        """wav [B, L] -> log-mel [B, T, num_mels] (get_mel, utils/audio_processor.py:460-468; frames are rows here)."""
+        wav = self._f32c(wav)
+        B, L = wav.shape
+        T = 1 + L // self.audio["hop_length"]
+        with torch.cuda.device(wav.device):
+            ws, need = self._enc_ws(B, L, True, wav.device)
+            mel = torch.empty(B, T, self.encoder_cfg["num_mels"], dtype=torch.float32, device=wav.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_encoder_mel(self.handle, _ptr(wav), _ptr(mel), B, L, _ptr(ws), need, ctypes.c_void_p(st)), "vs_encoder_mel")
+        return mel
+
+    def encoder_forward(self, mel):
+        """log-mel [B, T, num_mels] -> d-vectors [B, emb_dim] (SpeakerEncoder.forward, notebook :75-85)."""
+        mel = self._f32c(mel)
+        B, T, _ = mel.shape
+        with torch.cuda.device(mel.device):
+            ws, need = self._enc_ws(B, T, False, mel.device)
+            dvec = torch.empty(B, self.encoder_cfg["emb_dim"], dtype=torch.float32, device=mel.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_encoder_forward(self.handle, _ptr(mel), _ptr(dvec), B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_encoder_forward")
+        return dvec
+
+    def encoder_dvector(self, wav):
+        """wav [B, L] -> d-vectors [B, emb_dim]; the log-mel never leaves its 16-bit operand planes."""
+        wav = self._f32c(wav)
+        B, L = wav.shape
+        with torch.cuda.device(wav.device):
+            ws, need = self._enc_ws(B, L, True, wav.device)
+            dvec = torch.empty(B, self.encoder_cfg["emb_dim"], dtype=torch.float32, device=wav.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_encoder_dvector(self.handle, _ptr(wav), _ptr(dvec), B, L, _ptr(ws), need, ctypes.c_void_p(st)), "vs_encoder_dvector")
+        return dvec
+
     # ---- training (fp32, batch-statistics BatchNorm, full backward) ------------------------------
     PARAM_ORDER = tuple([k for l in range(8) for k in (f"conv.{CONV_IDX[l]}.weight", f"conv.{CONV_IDX[l]}.bias",
                                                         f"conv.{BN_IDX[l]}.weight", f"conv.{BN_IDX[l]}.bias")] +
