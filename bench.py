@@ -395,7 +395,17 @@ def extra_measurements(dev):
     ms = timed(lambda: eng.separate(wav, e2), 3)
     out["audio_e2e_config5"] = {"value": Bw / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "batch": Bw, "samples": 48000,
                                 "what": "waveform -> STFT (tcgen05 GEMM) -> CNN+BiLSTM+FC mask (fp16x3) -> mask*spec -> iSTFT (mixture phase) -> waveform"}
-    del eng, wav, e2
+    # ---- d-vector extraction: 3 s reference clips -> GE2E embedding, B = 128
+    from voicesplit_b200.speaker_encoder import SpeakerEncoder
+    enc = SpeakerEncoder(engine=eng)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_encoder_state_dict(1, "stress").items()})
+    enc = enc.to(dev)
+    ref_wav = torch.from_numpy(synth.make_reference_audio(128, 48000, 5)).to(dev)
+    ms = timed(lambda: enc.embed_wav(ref_wav), 5)
+    out["dvector_extract"] = {"value": 128 / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "batch": 128, "samples": 48000,
+                              "what": "waveform -> |STFT|^2 -> 40 mel -> log10 -> 6 windows x 3 x LSTM(768) (fp16x3 tcgen05, persistent recurrent "
+                                      "kernel) -> Linear(256) -> L2 normalise -> mean"}
+    del eng, wav, e2, enc, ref_wav
     torch.cuda.empty_cache()
     # ---- the honest GPU bar: the reference's own stock torch ops (restated in oracle/torch_port.py; the
     # reference tree cannot travel) on the SAME B200 through cuDNN/cuBLAS eager, strict fp32 and TF32-allowed

@@ -92,3 +92,29 @@ def test_separation_matches_full_oracle_pipeline(engine):
     si_snr = 10 * np.log10((ref ** 2).sum() / max((err ** 2).sum(), 1e-30))
     print(f"device vs oracle pipeline: SNR {si_snr:.1f} dB, max |diff| {np.abs(err).max():.2e}")
     assert si_snr > 50.0
+
+
+def test_separation_from_reference_audio_matches_full_oracle_pipeline(engine):
+    """Config 5 from raw audio on both inputs: reference clip -> GE2E d-vector (device) and mixture -> STFT -> mask ->
+    iSTFT, against the all-oracle chain (encoder_oracle + audio_oracle + torch_port) with the same weights."""
+    from oracle import encoder_oracle as eo, torch_port
+    from voicesplit_b200.speaker_encoder import SpeakerEncoder
+    dims = synth.make_dims(601, 256, 400, 600)
+    sd = synth.make_state_dict(dims, 3, "default")
+    esd = synth.make_encoder_state_dict(4, "default")
+    enc = SpeakerEncoder(engine=engine)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in esd.items()})
+    enc = enc.cuda()
+    mix = _signals(1, 20000, seed=12)
+    ref_clip = synth.make_reference_audio(1, 24000, 13)
+    dvec = enc.embed_wav(torch.from_numpy(ref_clip).cuda())
+    got = engine.separate(torch.from_numpy(mix).cuda(), dvec).cpu().numpy()[0]
+    d_ref = eo.speaker_encoder(esd, eo.get_mel(ref_clip[0])).astype(np.float32)[None]
+    assert np.abs(dvec.cpu().numpy() - d_ref).max() < 3e-4
+    S, ph = ao.wav2spec(mix[0])
+    mask = torch_port.forward(sd, S[None].astype(np.float32), d_ref, "mish").numpy()[0]
+    ref = ao.spec2wav(mask * S, ph)
+    err = got - ref
+    snr = 10 * np.log10((ref ** 2).sum() / max((err ** 2).sum(), 1e-30))
+    print(f"device vs oracle pipeline (d-vector from audio): SNR {snr:.1f} dB")
+    assert snr > 50.0
