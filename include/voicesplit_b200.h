@@ -222,6 +222,19 @@ int vs_sisnr_loss(vs_engine* e, const float* est_spec, const float* target_spec,
                   const int64_t* seq_len, float* loss_out, float* snr_out, float* grad_est, int32_t B, int32_t T,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- evaluation metrics on the device (utils/generic_utils.py:476-533, test.py:71) ----
+ *   vs_sisnr_wav  SiSNR_With_Pit on waveforms, one source per utterance (utils/generic_utils.py:417-474): est / target
+ *                 [B][L] fp32, seq_len [B] int64 -> loss = 20 - mean(snr) (device scalar) and snr [B] (required).
+ *                 NOTE validation() calls criterion(clean, est) - arguments swapped w.r.t. training;
+ *                 the caller chooses the order, the kernel treats its first waveform as the estimate.
+ *   vs_sdr        mir_eval.separation.bss_eval_sources(ref, est, compute_permutation=False)[0][0] per utterance
+ *                 (utils/generic_utils.py:511): 512-tap projection SDR in double precision; ref / est [B][L] fp32 -> [B]. */
+int vs_sisnr_wav(vs_engine* e, const float* est_wav, const float* target_wav, const int64_t* seq_len, float* loss_out,
+                 float* snr_out, int32_t B, int32_t L, void* stream);
+size_t vs_sdr_workspace_bytes(int32_t B, int32_t L);
+int vs_sdr(vs_engine* e, const float* ref_wav, const float* est_wav, float* sdr_out, int32_t B, int32_t L,
+           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- GE2E speaker encoder: the producer of the d-vector ---------------------
  * Replaces, for the extraction loop of notebooks/GE2E-Seungwonpark-ExtractSpeakerEmbedding-adaptado-para-openvoicefilter.py
  * (:141-143):  mel = ap.get_mel(wav)   (utils/audio_processor.py:456-468: |librosa.stft|^2 -> mel basis -> log10(. + 1e-6))

@@ -93,6 +93,9 @@ SIGNATURES = {
     "vs_encoder_mel": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_encoder_forward": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_encoder_dvector": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_sisnr_wav": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
+    "vs_sdr_workspace_bytes": (_SZ, [_I, _I]),
+    "vs_sdr": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
     "vs_conv_stack": (ctypes.c_int, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "vs_debug_conv_layer": (ctypes.c_int, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "vs_debug_lstm_head": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),

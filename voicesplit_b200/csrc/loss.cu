@@ -134,14 +134,15 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /*[32 * NV
 }
 
 // SiSNR_With_Pit for one source per utterance (utils/generic_utils.py:421-473 with C = 1) and its gradient.
-// wav rows [0, B) = estimates, rows [B, 2B) = targets.  One CTA per utterance.
-__global__ void __launch_bounds__(1024) k_sisnr(const float* __restrict__ wav, const long long* __restrict__ lens, int B, int L, float* __restrict__ snr_out,
+// est_wav / tgt_wav: [B][L].  One CTA per utterance.
+__global__ void __launch_bounds__(1024) k_sisnr(const float* __restrict__ est_wav, const float* __restrict__ tgt_wav, const long long* __restrict__ lens, int B,
+                                                int L, float* __restrict__ snr_out,
                                                 const float* __restrict__ wsq, elt16* __restrict__ uhi, elt16* __restrict__ ulo, int T, int win, int hop,
                                                 int lp, int half, int Lp) {
     __shared__ double sh[32 * 4];
     const int b = blockIdx.x;
-    const float* est = wav + (size_t)b * L;
-    const float* tgt = wav + (size_t)(B + b) * L;
+    const float* est = est_wav + (size_t)b * L;
+    const float* tgt = tgt_wav + (size_t)b * L;
     const long long len = lens[b];
     const int valid = len < 0 ? 0 : (len > L ? L : (int)len);       // get_mask: mask[i, :, len:] = 0
     const double n = (double)len;                                   // :431 num_samples is the raw length
@@ -353,13 +354,27 @@ int vs_sisnr_loss(vs_engine* e, const float* est_spec, const float* target_spec,
     int rc = loss_forward(e, s, w, est_spec, target_spec, phase, w.wav, B, T, st);
     if (rc != VS_OK) return rc;
     float* snr = snr_out ? snr_out : w.snr;
-    k_sisnr<<<B, 1024, 0, st>>>(w.wav, (const long long*)seq_len, B, w.Lout, snr, s->wsq, grad_est ? w.u_hi : nullptr, w.u_lo, T, s->win, s->hop,
+    k_sisnr<<<B, 1024, 0, st>>>(w.wav, w.wav + (size_t)B * w.Lout, (const long long*)seq_len, B, w.Lout, snr, s->wsq, grad_est ? w.u_hi : nullptr, w.u_lo, T, s->win, s->hop,
                                 (s->n_fft - s->win) / 2, s->n_fft / 2, w.Lp);
     VS_LAUNCH(e, KID_TR_MISC, st, cudaGetLastError());
     k_loss_mean<<<1, 256, 0, st>>>(snr, B, loss_out);
     VS_LAUNCH(e, KID_TR_MISC, st, cudaGetLastError());
     if (!grad_est) return VS_OK;
     return loss_backward_gemm(e, s, w, est_spec, phase, grad_est, B, T, st);
+}
+
+
+int vs_sisnr_wav(vs_engine* e, const float* est_wav, const float* target_wav, const int64_t* seq_len, float* loss_out, float* snr_out, int32_t B,
+                 int32_t L, void* stream) {
+    if (!e || !est_wav || !target_wav || !seq_len || !loss_out || !snr_out || B < 1 || L < 1) { set_error("bad argument"); return VS_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    e->launches = 0;
+    prof_begin(e, st);
+    k_sisnr<<<B, 1024, 0, st>>>(est_wav, target_wav, (const long long*)seq_len, B, L, snr_out, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0);
+    VS_LAUNCH(e, KID_TR_MISC, st, cudaGetLastError());
+    k_loss_mean<<<1, 256, 0, st>>>(snr_out, B, loss_out);
+    VS_LAUNCH(e, KID_TR_MISC, st, cudaGetLastError());
+    return VS_OK;
 }
 
 }  // extern "C"

@@ -253,6 +253,36 @@ class MaskEngine:
                                                _ptr(grad) if want_grad else None, B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_sisnr_loss")
         return loss, snr, grad
 
+    # ---- evaluation metrics (utils/generic_utils.py:476-533) ----------------------------------------------------
+    def sisnr_wav(self, est_wav, target_wav, seq_len):
+        """SiSNR_With_Pit on waveforms [B, L], one source each -> (loss [], snr [B]).  The first argument is the estimate."""
+        est, tgt = self._f32c(est_wav), self._f32c(target_wav)
+        if est.shape != tgt.shape or est.dim() != 2:
+            raise ValueError("estimate and target waveforms must both be [B, L]")      # generic_utils.py:426 assert
+        B, L = est.shape
+        lens = seq_len.detach().reshape(-1).to(device=est.device, dtype=torch.int64).contiguous()
+        with torch.cuda.device(est.device):
+            loss = torch.empty((), dtype=torch.float32, device=est.device)
+            snr = torch.empty(B, dtype=torch.float32, device=est.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_sisnr_wav(self.handle, _ptr(est), _ptr(tgt), _ptr(lens), _ptr(loss), _ptr(snr), B, L, ctypes.c_void_p(st)),
+                        "vs_sisnr_wav")
+        return loss, snr
+
+    def sdr(self, ref_wav, est_wav):
+        """bss_eval_sources(ref, est, False)[0][0] per utterance: ref, est [B, L] -> SDR [B] in dB."""
+        ref, est = self._f32c(ref_wav), self._f32c(est_wav)
+        if ref.shape != est.shape or ref.dim() != 2:
+            raise ValueError("reference and estimate waveforms must both be [B, L]")
+        B, L = ref.shape
+        with torch.cuda.device(ref.device):
+            need = int(self.lib.vs_sdr_workspace_bytes(B, L))
+            ws = torch.empty(need, dtype=torch.uint8, device=ref.device)
+            out = torch.empty(B, dtype=torch.float32, device=ref.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(self.lib.vs_sdr(self.handle, _ptr(ref), _ptr(est), _ptr(out), B, L, _ptr(ws), need, ctypes.c_void_p(st)), "vs_sdr")
+        return out
+
     # ---- GE2E speaker encoder: wav -> log-mel -> 3 x LSTM -> d-vector (notebooks/GE2E-...-openvoicefilter.py:63-85,141-143) ----
     def configure_encoder(self, num_mels=40, lstm_layers=3, lstm_hidden=768, emb_dim=256, window=80, stride=40, sample_rate=16000):
         """Needs configure_audio() first: the mel front end shares its STFT (n_fft / hop / win)."""
