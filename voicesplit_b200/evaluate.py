@@ -25,12 +25,16 @@ def _t(a, device, dtype=torch.float32):
     return t.to(device=device, dtype=dtype)
 
 
+def _np(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
 def _batches(testloader, batch_size):
     """Group loader items (each `batch[0]` is one item, utils/dataset.py eval_collate_fn) by spectrogram / waveform shape."""
     groups = {}
     for batch in testloader:
         item = batch[0] if isinstance(batch, (list, tuple)) and isinstance(batch[0], (list, tuple)) else batch
-        key = (tuple(item[2].shape), int(np.asarray(item[3]).shape[-1]))
+        key = (tuple(item[2].shape), int(tuple(item[3].shape)[-1]))
         groups.setdefault(key, []).append(item)
         if len(groups[key]) == batch_size:
             yield groups.pop(key)
@@ -78,7 +82,7 @@ def validation(criterion, ap, model, testloader, tensorboard=None, step=0, cuda=
                 test_loss, sdr0 = float(item_loss[0]), float(sdr[0])
                 if tensorboard is not None:
                     it = items[0]
-                    tensorboard.log_evaluation(test_loss, sdr0, np.asarray(it[4]), np.asarray(it[3]), est_wav[0].cpu().numpy(),
+                    tensorboard.log_evaluation(test_loss, sdr0, _np(it[4]), _np(it[3]), est_wav[0].cpu().numpy(),
                                                mixed_spec[0].cpu().numpy().T, clean_spec[0].cpu().numpy().T, est_mag[0].cpu().numpy().T,
                                                est_mask[0].cpu().numpy().T, step)
                 print("Validation Loss:", test_loss)
