@@ -303,6 +303,9 @@ def main():
                     "avg_launch_ms": avg, "algorithmic_flops_per_launch": fl["conv5x5_layer"] * B,
                     "algorithmic_bytes_per_launch": B * T * padded_f(F) * 64 * 2 * (2 if passes == 3 else 1) * 2 if passes else None,
                     "mma_passes": passes, "tensor_pipe_frac_incl_passes": (ach * passes / peak) if passes else None,
+                    # what the tensor pipe actually executes: algorithmic flops x passes x 6/5 (five filter taps occupy six M=128 slots)
+                    "issued_tflops": (ach * passes * 1.2) if passes else None,
+                    "issued_frac_of_peak": (ach * passes * 1.2 / peak) if passes else None,
                     "note": "fp32 mode runs on CUDA cores (no tensor pipe)" if prec == "fp32" else
                             "frac counts ALGORITHMIC flops; the faithful mode issues 3 MMA passes (hi*hi + lo*hi + hi*lo) and pads 5 taps to 6 slots"}
         line = {"metric": "utterances/s (601-frame, 257-bin spectrogram) masked", "value": value, "unit": "utterances/s",
