@@ -172,6 +172,13 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_plane(const float* __restr
                                                             const float* __restrict__ gamma, const double* __restrict__ sums, double count,
                                                             float* __restrict__ dz, int F, int Fp, long long npix,
                                                             elt16* __restrict__ dhi, elt16* __restrict__ dlo) {
+    // per-channel constants once per block (the double divisions used to run per element): m1 = S1/N, m2 = S2/N, g = gamma rstd
+    __shared__ float cm1[64], cm2[64], cg[64];
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        cm1[c] = (float)(sums[c] / count); cm2[c] = (float)(sums[64 + c] / count); cg[c] = gamma[c] * stat[64 + c];
+    }
+    __syncthreads();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // float4 index over [pixels][16]
     if (i >= npix * 16) return;
     const int c4 = (int)(i & 15) * 4;
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_plane(const float* __restr
             const float mean = stat[c], rstd = stat[64 + c];
             const float du = dd[k] * act_grad<ACT>(fmaf(zz[k], stat[128 + c], stat[192 + c]));
             const float xh = (zz[k] - mean) * rstd;
-            o[k] = gamma[c] * rstd * (du - (float)(sums[c] / count) - xh * (float)(sums[64 + c] / count));
+            o[k] = cg[c] * (du - cm1[c] - xh * cm2[c]);
         }
     }
     if (dz) reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
