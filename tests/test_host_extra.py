@@ -1,0 +1,65 @@
+"""Host-side logic of the section-8f components that needs no GPU: state_dict layout of the speaker encoder, batch grouping
+of the evaluation driver, and the torch criterion against the loss oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle
+from voicesplit_b200 import evaluate, losses, synth
+from voicesplit_b200.speaker_encoder import SpeakerEncoder
+
+CKPT = "/root/reference/notebooks/embedder.pt"
+
+
+def test_speaker_encoder_state_dict_layout():
+    enc = SpeakerEncoder()
+    want = {}
+    for l in range(3):
+        want[f"lstm.weight_ih_l{l}"] = (3072, 40 if l == 0 else 768)
+        want[f"lstm.weight_hh_l{l}"] = (3072, 768)
+        want[f"lstm.bias_ih_l{l}"] = (3072,)
+        want[f"lstm.bias_hh_l{l}"] = (3072,)
+    want["proj.linear_layer.weight"] = (256, 768)
+    want["proj.linear_layer.bias"] = (256,)
+    got = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    assert got == want
+    # the synthetic weights used by the parity tests follow the same layout
+    assert {k: tuple(v.shape) for k, v in synth.make_encoder_state_dict(0).items()} == want
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_encoder_state_dict(0).items()}, strict=True)
+
+
+@pytest.mark.skipif(not os.path.isfile(CKPT), reason="reference checkpoint not present")
+def test_speaker_encoder_loads_the_reference_checkpoint_unchanged():
+    enc = SpeakerEncoder(40, 3, 768, 80, 40)                      # the notebook's positional arguments (:88)
+    missing = enc.load_state_dict(torch.load(CKPT, map_location="cpu"), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+
+
+def test_speaker_encoder_without_engine_fails_loudly():
+    with pytest.raises(RuntimeError):
+        SpeakerEncoder()(torch.zeros(40, 100))                    # CPU tensor: no silent fallback
+
+
+def test_eval_batches_group_by_shape_and_keep_every_item():
+    def item(T, L, tag):
+        return [(tag, None, np.zeros((T, 5), np.float32), np.zeros(L, np.float32), None, None, None)]
+    loader = [item(10, 100, 0), item(10, 100, 1), item(12, 100, 2), item(10, 100, 3), item(10, 90, 4), item(10, 100, 5), item(10, 100, 6)]
+    batches = list(evaluate._batches(loader, 3))
+    tags = sorted(it[0] for b in batches for it in b)
+    assert tags == list(range(7))
+    for b in batches:
+        assert len(b) <= 3
+        assert len({(it[2].shape, it[3].shape) for it in b}) == 1      # one spectrogram / waveform shape per batch
+    assert [it[0] for it in batches[0]] == [0, 1, 3]                     # a full group is emitted as soon as it fills up
+
+
+def test_torch_criterion_matches_loss_oracle_for_one_source():
+    rng = np.random.Generator(np.random.PCG64(3))
+    est, tgt = rng.standard_normal((4, 500)), rng.standard_normal((4, 500))
+    est = 0.6 * tgt + 0.4 * est
+    lens = torch.tensor([500, 321, 500, 77])
+    a = losses.si_snr_with_pit(torch.from_numpy(est)[:, None], torch.from_numpy(tgt)[:, None], lens)
+    b, _ = loss_oracle.si_snr_c1(torch.from_numpy(est), torch.from_numpy(tgt), lens)
+    assert abs(float(a) - float(b)) < 1e-9
