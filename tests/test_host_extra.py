@@ -63,3 +63,11 @@ def test_torch_criterion_matches_loss_oracle_for_one_source():
     a = losses.si_snr_with_pit(torch.from_numpy(est)[:, None], torch.from_numpy(tgt)[:, None], lens)
     b, _ = loss_oracle.si_snr_c1(torch.from_numpy(est), torch.from_numpy(tgt), lens)
     assert abs(float(a) - float(b)) < 1e-9
+
+
+def test_sdr_workspace_is_a_pure_host_query():
+    from voicesplit_b200 import _cabi
+    lib = _cabi.load()
+    a, b, c = (int(lib.vs_sdr_workspace_bytes(B, L)) for B, L in ((1, 48000), (8, 48000), (8, 96000)))
+    assert 0 < a < b < c
+    assert int(lib.vs_sdr_workspace_bytes(0, 48000)) == 0 and int(lib.vs_sdr_workspace_bytes(4, 0)) == 0
