@@ -1,6 +1,8 @@
 """Host-side logic of the section-8f components that needs no GPU: state_dict layout of the speaker encoder, batch grouping
 of the evaluation driver, and the torch criterion against the loss oracle."""
 import os
+import shutil
+import subprocess
 
 import numpy as np
 import pytest
@@ -71,3 +73,13 @@ def test_sdr_workspace_is_a_pure_host_query():
     a, b, c = (int(lib.vs_sdr_workspace_bytes(B, L)) for B, L in ((1, 48000), (8, 48000), (8, 96000)))
     assert 0 < a < b < c
     assert int(lib.vs_sdr_workspace_bytes(0, 48000)) == 0 and int(lib.vs_sdr_workspace_bytes(4, 0)) == 0
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no C compiler")
+def test_public_header_is_plain_c_and_cxx():
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "voicesplit_b200.h")
+    for args in (["gcc", "-std=c99", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c"], ["g++", "-std=c++17", "-Werror", "-fsyntax-only", "-x", "c++"]):
+        if shutil.which(args[0]) is None:
+            continue
+        r = subprocess.run(args + [hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

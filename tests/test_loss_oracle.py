@@ -49,3 +49,27 @@ def test_lengths_mask_and_q1_differs_from_corrected():
     assert abs(a["loss"] - c["loss"]) > 1e-2
     # clamp: no gradient where the estimate lies outside [0, 1]
     assert np.all(a["grad_est"][(est < 0) | (est > 1)] == 0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/utils"), reason="reference tree not present")
+def test_loss_oracle_against_the_live_reference_on_a_fresh_case():
+    """Beyond the committed goldens: run the unmodified reference chain here (build container only) on another shape."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_make_loss_golden", os.path.join(os.path.dirname(__file__), "golden", "make_loss_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    apm, gu = gen.load_reference_audio_processor()
+    n_fft, hop, win, B, T = 256, 64, 128, 3, 23
+    ap = apm.openVoiceFilterAudioProcessor(sample_rate=16000, n_fft=n_fft, num_freq=n_fft // 2 + 1, hop_length=hop, win_length=win, preemphasis=0.97,
+                                           power=1.5, min_level_db=-100.0, ref_level_db=20.0, num_mels=40, griffin_lim_iters=60)
+    est, tgt, phase = loss_inputs(n_fft, B, T, 77)
+    lens = np.array([hop * (T - 1), 1000, 333], dtype=np.int64)
+    e = torch.from_numpy(est).requires_grad_(True)
+    out = ap.torch_inv_spectrogram(e, torch.from_numpy(phase))
+    ref = ap.torch_inv_spectrogram(torch.from_numpy(tgt), torch.from_numpy(phase))
+    loss = gu.SiSNR_With_Pit()(out[:, None, :], ref[:, None, :], torch.from_numpy(lens))
+    loss.backward()
+    r = loss_oracle.loss_and_grad(est, tgt, phase, lens, n_fft, hop, win, mode="q1")
+    assert abs(r["loss"] - float(loss)) <= 2e-4
+    gs = float(e.grad.abs().max())
+    assert np.abs(r["grad_est"] - e.grad.numpy()).max() <= 2e-4 * gs
