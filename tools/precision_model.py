@@ -1,0 +1,114 @@
+"""CPU model of the conv stack's operand-splitting arithmetic (no GPU): which mask error does a given pass scheme cost?
+
+The tensor-core conv computes  x*w  as  hi*hi + lo_x*hi_w + hi_x*lo_w  with 16-bit hi/lo planes and fp32 accumulation
+(DESIGN.md 4.1).  This tool emulates that per layer in float64 (splitting exactly as the device does, accumulating
+exactly), keeps everything else exact, and reports the mask error against the float64 forward on the stress weights -
+for the shipped schemes (cross-check against the measured device errors in DESIGN.md 4.2) and for candidates:
+  fp16x2_w / fp16x2_x : drop one correction pass
+  fp16+f8x2           : both correction passes with e4m3 operands (kind::f8f6f4, 2x rate) - DESIGN.md section 12, item 1a
+  fp16+f8x1           : only lo_x * w in e4m3
+
+    python tools/precision_model.py [--frames 120] [--freq 257]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from voicesplit_b200 import synth  # noqa: E402
+
+CONVS = ((1, 2, (3, 3, 0, 0), 1), (5, 6, (0, 0, 3, 3), 1), (9, 10, (2, 2, 2, 2), 1), (13, 14, (2, 2, 4, 4), 2),
+         (17, 18, (2, 2, 8, 8), 4), (21, 22, (2, 2, 16, 16), 8), (25, 26, (2, 2, 32, 32), 16), (28, 29, None, 1))
+
+
+def q16(v, dtype):
+    return v.to(dtype).to(torch.float64)
+
+
+def split(v, dtype):
+    hi = q16(v, dtype)
+    return hi, q16(v - hi, dtype)
+
+
+def q8(v):
+    """e4m3 with a per-tensor power-of-two scale (what a packed operand plane would carry)."""
+    m = float(v.abs().max())
+    if m == 0.0:
+        return v
+    s = 2.0 ** np.floor(np.log2(448.0 / m))
+    return (v * s).to(torch.float8_e4m3fn).to(torch.float64) / s
+
+
+def conv_scheme(x, w, dil, scheme):
+    c = lambda a, b: F.conv2d(a, b, None, dilation=(dil, 1))
+    if scheme == "exact":
+        return c(x, w)
+    base = torch.bfloat16 if scheme.startswith("bf16") else torch.float16
+    xc = x.clamp(-60000.0, 60000.0) if base is torch.float16 else x
+    ws = 2.0 ** (9 - np.ceil(np.log2(float(w.abs().max())))) if base is torch.float16 else 1.0     # power-of-two weight pre-scale
+    xh, xl = split(xc, base)
+    wh, wl = split(w * ws, base)
+    out = c(xh, wh)
+    if scheme in ("fp16x3", "bf16x3"):
+        out = out + c(xl, wh) + c(xh, wl)
+    elif scheme == "fp16x2_w":
+        out = out + c(xl, wh)
+    elif scheme == "fp16x2_x":
+        out = out + c(xh, wl)
+    elif scheme == "fp16+f8x2":
+        out = out + c(q8(xl), q8(wh)) + c(q8(xh), q8(wl))
+    elif scheme == "fp16+f8x1":
+        out = out + c(q8(xl), q8(wh)) + c(xh, wl)
+    elif scheme not in ("fp16", "bf16"):
+        raise ValueError(scheme)
+    return out / ws
+
+
+def forward(sd, x, emb, scheme):
+    t = lambda k: torch.from_numpy(np.asarray(sd[k])).to(torch.float64)
+    h = torch.from_numpy(x).to(torch.float64).unsqueeze(1)
+    for i, (ci, bi, pad, dil) in enumerate(CONVS):
+        if pad is not None:
+            h = F.pad(h, pad)
+        on_tc = 1 <= i <= 6                                       # cnn2..cnn7 run on k_conv_tc; cnn1 / cnn8 on CUDA cores in fp32
+        z = conv_scheme(h, t(f"conv.{ci}.weight"), dil, scheme if on_tc else "exact") + t(f"conv.{ci}.bias").view(1, -1, 1, 1)
+        z = F.batch_norm(z, t(f"conv.{bi}.running_mean"), t(f"conv.{bi}.running_var"), t(f"conv.{bi}.weight"), t(f"conv.{bi}.bias"), training=False, eps=1e-5)
+        h = z * torch.tanh(F.softplus(z))
+    B, C, T, Fq = h.shape
+    feat = torch.cat((h.permute(0, 2, 1, 3).reshape(B, T, C * Fq), torch.from_numpy(emb).to(torch.float64)[:, None, :].expand(B, T, emb.shape[1])), dim=2)
+    H = sd["lstm.weight_hh_l0"].shape[1]
+    flat = [t(f"lstm.{n}_l0{s}") for s in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    z0 = torch.zeros(2, B, H, dtype=torch.float64)
+    out, _, _ = torch._VF.lstm(feat, (z0, z0), flat, True, 1, 0.0, False, True, True)
+    y = F.linear(torch.relu(out), t("fc1.weight"), t("fc1.bias"))
+    return torch.sigmoid(F.linear(torch.relu(y), t("fc2.weight"), t("fc2.bias"))).numpy()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=120)
+    ap.add_argument("--freq", type=int, default=257)
+    ap.add_argument("--flavour", default="stress")
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    dims = synth.make_dims(args.freq, 256, 400, 600)
+    sd = synth.make_state_dict(dims, 0, args.flavour)
+    x, emb = synth.make_inputs(2, args.frames, dims, 5)
+    with torch.no_grad():
+        ref = forward(sd, x, emb, "exact")
+        rows = {}
+        for scheme, passes in (("fp16x3", 3), ("bf16x3", 3), ("fp16+f8x1", 2.5), ("fp16+f8x2", 2), ("fp16x2_w", 2), ("fp16x2_x", 2), ("fp16", 1), ("bf16", 1)):
+            d = np.abs(forward(sd, x, emb, scheme) - ref)
+            rows[scheme] = {"pass_equivalents": passes, "mask_max_abs": float(d.max()), "mask_mae": float(d.mean())}
+            print(f"{scheme:10s} passes {passes:<4} max {d.max():.2e}  mae {d.mean():.2e}", flush=True)
+    print(json.dumps({"frames": args.frames, "freq": args.freq, "weights": args.flavour, "model": "conv layers cnn2..cnn7 emulated, rest exact (float64)",
+                      "schemes": rows}))
+
+
+if __name__ == "__main__":
+    main()
