@@ -1,13 +1,13 @@
 // Stand-alone probe for the fp8-correction candidate: can the two 2^-11 correction passes of
 // the conv run as tcgen05.mma kind::f8f6f4 (e4m3 operands, 2x the rate of kind::f16) INTO THE SAME fp32 TMEM accumulator as
 // the fp16 main pass, with the row-shifted window trick of k_conv_tc on 64-byte pixel rows?
-// Built here (nvcc sm_100a) and meant to be run on the B200 box (NOT yet run: written at the end of round 1 when the GPU budget
-// was spent - treat every expectation below as a hypothesis):
+// Built here (nvcc sm_100a), run on the B200 box via gpurun; results of the round-1 run are in profiles/r01_f8_probe.txt
+// (all checked cases exact; ~129 cycles per e4m3 MMA at N = 256, 171 back to back on 64-byte rows):
 //   case 1  e4m3 x e4m3, no-swizzle K-major layout, K = 64 (two K = 32 MMAs), N = 64 and 256            -> exact vs CPU
 //   case 2  128-byte rows (128 fp8 per row), 128B swizzle, window start shifted by 0..9 rows, base_offset 0 -> exact vs CPU
 //   case 3  64-byte rows (one pixel = 64 channels), 64B swizzle (layout code 4, 8-row atom = 512 B), shifted windows
 //   case 4  kind::f16 MMA followed by kind::f8f6f4 MMAs into one accumulator (accumulate = 1)            -> sum of both products
-//   case 5  cycles per MMA: f8 at N = 256 (hypothesis: 64, half of f16's 128), and f16 / f8 interleaved
+//   case 5  cycles per MMA: f8 at N = 256 (K = 32 per instruction, so equal cycles = twice the fp16 rate), and f16 / f8 interleaved
 // Operands are small integers / powers of two so that every product and sum is exact in fp32 (no tolerance needed).
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
