@@ -7,6 +7,7 @@
 //   case 2  128-byte rows (128 fp8 per row), 128B swizzle, window start shifted by 0..9 rows, base_offset 0 -> exact vs CPU
 //   case 3  64-byte rows (one pixel = 64 channels), 64B swizzle (layout code 4, 8-row atom = 512 B), shifted windows
 //   case 4  kind::f16 MMA followed by kind::f8f6f4 MMAs into one accumulator (accumulate = 1)            -> sum of both products
+//   case 6  the 64-byte-row strip filled by TMA (UINT16 x 32 per row, SWIZZLE_64B, box of 136 rows, negative start row = zero fill)
 //   case 5  cycles per MMA: f8 at N = 256 (K = 32 per instruction, so equal cycles = twice the fp16 rate), and f16 / f8 interleaved
 // Operands are small integers / powers of two so that every product and sum is exact in fp32 (no tolerance needed).
 #include <cuda_fp16.h>
@@ -14,6 +15,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #include "../voicesplit_b200/csrc/sm100_ptx.cuh"
@@ -46,6 +48,8 @@ struct F8Args {
     int with_f16;         // case 4: one fp16 K = 64 product first
     int iters, interleave;
     long long* cycles;
+    int tma_fill;         // case 6: the B strip comes from TMA (64B swizzle, 64-byte rows) starting at global row `tma_row0` (may be < 0)
+    int tma_row0;
 };
 
 // byte offset of 16-byte chunk c of row r in the given layout (rows of `rowbytes` bytes, `rows` rows in the tile)
@@ -55,17 +59,17 @@ __device__ __forceinline__ uint32_t chunk_off(int layout, int r, int c, int rowb
     return (uint32_t)(c * (rows * 16) + r * 16);                                     // no swizzle: [chunk][row] core-matrix columns
 }
 
-__global__ void __launch_bounds__(128, 1) f8_probe_kernel(F8Args a) {
+__global__ void __launch_bounds__(128, 1) f8_probe_kernel(F8Args a, const __grid_constant__ CUtensorMap tmB) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                 // 128 x K bytes (<= 16 KB)
     uint8_t* sB = smem + 16384;         // strip_rows x K bytes (<= 34 KB)
     uint8_t* sA16 = smem + 16384 + 36864;   // 128 x 128 B fp16, 128B swizzle
     uint8_t* sB16 = sA16 + 16384;           // N x 128 B
-    __shared__ uint64_t bar_mma;
+    __shared__ uint64_t bar_mma, bar_load;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+    if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_load, 1); fence_barrier_init(); }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
@@ -76,9 +80,11 @@ __global__ void __launch_bounds__(128, 1) f8_probe_kernel(F8Args a) {
         const int r = idx / cpr, c = idx % cpr;
         *reinterpret_cast<uint4*>(sA + chunk_off(a.layout, r, c, a.K, 128)) = reinterpret_cast<const uint4*>(a.A8)[idx];
     }
-    for (int idx = tid; idx < a.strip_rows * cpr; idx += 128) {
-        const int r = idx / cpr, c = idx % cpr;
-        *reinterpret_cast<uint4*>(sB + chunk_off(a.layout, r, c, a.K, a.strip_rows)) = reinterpret_cast<const uint4*>(a.B8)[idx];
+    if (!a.tma_fill) {
+        for (int idx = tid; idx < a.strip_rows * cpr; idx += 128) {
+            const int r = idx / cpr, c = idx % cpr;
+            *reinterpret_cast<uint4*>(sB + chunk_off(a.layout, r, c, a.K, a.strip_rows)) = reinterpret_cast<const uint4*>(a.B8)[idx];
+        }
     }
     if (a.with_f16) {
         for (int idx = tid; idx < 128 * 8; idx += 128) {
@@ -92,6 +98,13 @@ __global__ void __launch_bounds__(128, 1) f8_probe_kernel(F8Args a) {
     }
     fence_proxy_async();
     __syncthreads();
+    if (a.tma_fill) {   // rows tma_row0 .. tma_row0 + strip_rows of the global [rows][64 B] plane; rows outside are zero-filled
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_load, (uint32_t)(a.strip_rows * 64));
+            for (int done = 0; done < a.strip_rows; done += 136) tma_load_2d(sB + done * 64, &tmB, &bar_load, 0, a.tma_row0 + done);
+        }
+        mbar_wait(&bar_load, 0);
+    }
 
     long long t0 = 0;
     if (tid == 0) {
@@ -147,8 +160,9 @@ static float from_e4m3(uint8_t b) {
     return __half2float(*reinterpret_cast<__half*>(&h));
 }
 
-static int run_case(const char* name, int N, int K, int layout, int shift, int with_f16, int iters, int interleave, bool check) {
-    const int strip = N + 16;
+static int run_case(const char* name, int N, int K, int layout, int shift, int with_f16, int iters, int interleave, bool check, int tma_fill = 0,
+                    int tma_row0 = 0) {
+    const int strip = tma_fill ? 272 : N + 16;          // TMA case: two boxes of 136 rows
     std::vector<uint8_t> A8((size_t)128 * K), B8((size_t)strip * K);
     std::vector<__half> A16(128 * 64), B16((size_t)N * 64);
     srand(1234 + N + K + layout + shift);
@@ -162,10 +176,17 @@ static int run_case(const char* name, int N, int K, int layout, int shift, int w
     cudaMalloc(&dD, (size_t)128 * N * 4); cudaMalloc(&dC, 8);
     cudaMemcpy(dA8, A8.data(), A8.size(), cudaMemcpyHostToDevice); cudaMemcpy(dB8, B8.data(), B8.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dA16, A16.data(), A16.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB16, B16.data(), B16.size() * 2, cudaMemcpyHostToDevice);
-    F8Args a{dA8, dB8, dA16, dB16, dD, N, K, strip, shift, layout, with_f16, iters, interleave, dC};
+    F8Args a{dA8, dB8, dA16, dB16, dD, N, K, strip, shift, layout, with_f16, iters, interleave, dC, tma_fill, tma_row0};
+    CUtensorMap tmB;
+    memset(&tmB, 0, sizeof(tmB));
+    if (tma_fill) {   // TMA only moves bits: 64 bytes per row = 32 uint16, 64B swizzle, box of 136 rows
+        uint64_t dims[2] = {32, (uint64_t)strip}, strides[1] = {64};
+        uint32_t box[2] = {32, 136};
+        if (!make_tmap_bf16(&tmB, dB8, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) { printf("tensor map failed\n"); return 1; }
+    }
     const int smem = 1024 + 16384 + 36864 + 16384 + 32768;
     cudaFuncSetAttribute(f8_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    f8_probe_kernel<<<1, 128, smem>>>(a);
+    f8_probe_kernel<<<1, 128, smem>>>(a, tmB);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%-44s CUDA error: %s\n", name, cudaGetErrorString(e)); return 1; }
     std::vector<float> D((size_t)128 * N);
@@ -176,7 +197,9 @@ static int run_case(const char* name, int N, int K, int layout, int shift, int w
         for (int m = 0; m < 128; ++m)
             for (int n = 0; n < N; ++n) {
                 double s = 0.0;
-                for (int k = 0; k < K; ++k) s += (double)from_e4m3(A8[(size_t)m * K + k]) * from_e4m3(B8[(size_t)(n + shift) * K + k]);
+                const int brow = n + shift + (tma_fill ? tma_row0 : 0);      // global row of the plane this window row maps to
+                for (int k = 0; k < K; ++k)
+                    s += (double)from_e4m3(A8[(size_t)m * K + k]) * ((brow >= 0 && brow < strip) ? from_e4m3(B8[(size_t)brow * K + k]) : 0.f);
                 s *= iters;
                 if (with_f16)
                     for (int k = 0; k < 64; ++k) s += (double)__half2float(A16[m * 64 + k]) * __half2float(B16[(size_t)n * 64 + k]) * (interleave ? iters : 1);
@@ -198,6 +221,8 @@ int main() {
     for (int sh : {0, 1, 2, 3, 4, 7, 9}) fails += run_case("3 e4m3 64B swizzle (64-byte pixel rows)", 256, 64, 4, sh, 0, 1, 0, true);
     fails += run_case("4 fp16 main + e4m3 correction, one accumulator", 256, 64, 4, 2, 1, 1, 0, true);
     fails += run_case("4 fp16 + e4m3, 128B rows", 256, 128, 2, 2, 1, 1, 0, true);
+    for (int sh : {0, 3, 8}) fails += run_case("6 TMA-filled 64B-swizzle strip, rows from -5", 256, 64, 4, sh, 0, 1, 0, true, 1, -5);
+    fails += run_case("6 TMA-filled strip + fp16 main pass", 256, 64, 4, 2, 1, 1, 0, true, 1, 3);
     run_case("5 timing e4m3 N=256 (64B rows)", 256, 64, 4, 0, 0, 256, 0, false);
     run_case("5 timing e4m3 N=256 (128B rows)", 256, 128, 2, 0, 0, 128, 0, false);
     run_case("5 timing fp16 + e4m3 interleaved", 256, 64, 4, 0, 1, 128, 1, false);
