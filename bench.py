@@ -268,8 +268,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     # ---- the single-pass fast mode, reported next to its measured error (never as the headline)
     fast = None
-    if prec in ("fp16x3", "bf16x3"):
-        fp = prec[:-2]
+    if prec in ("fp16x3", "bf16x3", "fp16_f8c"):
+        fp = prec[:4]
         gotf = eng.forward(x[:nb], emb[:nb], precision=fp)
         for _ in range(2):
             eng.forward(x, emb, precision=fp, want_masked=True)
@@ -288,7 +288,7 @@ def main():
         if all(v is not None for v in conv_ms):
             avg = float(np.mean(conv_ms))
             ach = fl["conv5x5_layer"] * B / (avg / 1e3) / 1e12
-            passes = {"bf16x3": 3, "fp16x3": 3, "bf16": 1, "fp16": 1}.get(prec)
+            passes = {"bf16x3": 3, "fp16x3": 3, "fp16_f8c": 2, "bf16": 1, "fp16": 1}.get(prec)
             peak = peaks["bf16_tflops_sustained"]
             traffic = None
             prof = os.path.join(ROOT, "profiles", "r01_conv_tc_summary.json")
@@ -301,7 +301,7 @@ def main():
                     "traffic_source": "profiles/r01_conv_tc_summary.json (ncu --set full, scaled per utterance)" if traffic else None,
                     "peak_source": peaks["source"] + ", sustained 16-bit dense (cuBLAS bf16; fp16 runs on the same pipe)",
                     "avg_launch_ms": avg, "algorithmic_flops_per_launch": fl["conv5x5_layer"] * B,
-                    "algorithmic_bytes_per_launch": B * T * padded_f(F) * 64 * 2 * (2 if passes == 3 else 1) * 2 if passes else None,
+                    "algorithmic_bytes_per_launch": B * T * padded_f(F) * 64 * 2 * (2 if passes >= 2 else 1) * 2 if passes else None,
                     "mma_passes": passes, "tensor_pipe_frac_incl_passes": (ach * passes / peak) if passes else None,
                     # what the tensor pipe actually executes: algorithmic flops x passes x 6/5 (five filter taps occupy six M=128 slots)
                     "issued_tflops": (ach * passes * 1.2) if passes else None,
@@ -313,6 +313,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16x3": "bf16x3 (split-bf16 operands hi+lo, 3 MMAs, fp32 accumulate)",
                           "fp16x3": "fp16x3 (split-fp16 operands hi+lo, 3 MMAs, fp32 accumulate)",
+                          "fp16_f8c": "fp16 + e4m3 correction (conv: 4 f16 + 4 f8f6f4 MMAs per tap pair, fp32 accumulate; LSTM/FC fp16x3)",
                           "bf16": "bf16", "fp16": "f16", "fp32": "f32"}[prec],
                 "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "utterances/s", "ms_per_step": e2e_ms / args.steps,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 1
+#define VS_ABI_VERSION 2
 
 #define VS_OK 0
 #define VS_ERR_INVALID (-1)     /* bad argument / unsupported shape */
@@ -53,6 +53,13 @@ extern "C" {
  *           activations are clamped to +-60000 before conversion. */
 #define VS_PREC_FP16X3 3
 #define VS_PREC_FP16 4
+/*   FP16_F8C: the conv stack (97 % of the tensor-core work) keeps every activation as fp16 `hi` plus a 128-byte e4m3
+ *           correction row [2^8 (x - hi) | 2^-2 hi] and every weight as fp16 `hi` plus [2^-8 w_hi | 2^2 w_lo]; per filter-tap
+ *           pair it issues the fp16 product (4 kind::f16 MMAs) and ONE fp8 product over that 128-byte K axis (4 kind::f8f6f4
+ *           MMAs at twice the rate) = x_lo w_hi + x_hi w_lo, into the same fp32 TMEM accumulator: 8 MMA slots instead of the
+ *           12 of FP16X3, correction terms carried with 4 significant bits (relative operand error ~2^-15).  LSTM input
+ *           projection, recurrence and FC head run as FP16X3. */
+#define VS_PREC_FP16_F8C 5
 
 typedef struct vs_engine vs_engine;
 
@@ -140,7 +147,7 @@ int vs_conv_stack(vs_engine* e, const float* x, float* conv_out, int32_t B, int3
  * place - the tensors of the module's own buffers.  It keeps what the backward needs in `workspace`
  * (vs_train_workspace_bytes), which must stay untouched until vs_train_backward has run.
  * vs_train_backward consumes d(loss)/d(mask) and writes the gradient of every parameter in the
- * reference's layouts (vs_grads mirrors vs_params) plus, optionally, d(loss)/d(emb).  Parameters must
+ * reference's layouts (vs_grads mirrors vs_params) plus, optionally, d(loss)/d(emb) and d(loss)/d(x).  Parameters must
  * have been loaded with vs_engine_load_params since their last change. */
 typedef struct vs_train_state {
     float* running_mean[8];
@@ -165,11 +172,29 @@ typedef struct vs_grads {
 /* The conv forward and data-gradient of the training path run on the tcgen05 conv kernel by default
  * (fp16x3 activations, bf16x3 gradients: fp32-grade, no loss scaling); 0 selects the fp32 CUDA-core convs. */
 int vs_engine_set_train_tensor_cores(vs_engine* e, int32_t enabled);
+
+/* Data-parallel training hooks.  Both callbacks run on the calling host thread in the middle of
+ * vs_train_forward / vs_train_backward and must only ENQUEUE work that is ordered after everything already enqueued on `stream`
+ * (an NCCL collective issued from that stream, or from a side stream that waits on an event recorded there); they return 0 or
+ * a non-zero error code, which aborts the call with VS_ERR_STATE.
+ *   vs_stat_allreduce_fn  SyncBN: sum `count` doubles on the device, in place, across the `world_size` ranks.  Called once per
+ *                         BatchNorm layer in the forward (per-channel sum z, sum z^2) and once in the backward (sum du,
+ *                         sum du xhat); the engine then divides by world_size x the local element count, so every rank
+ *                         normalises with the statistics of the CONCATENATED batch - the reference's single-process semantics
+ *                         (train.py:84-111 with plain nn.BatchNorm2d).  fn = NULL (default): per-rank statistics.
+ *   vs_backward_hook_fn   stage VS_BWD_STAGE_LSTM_FC_DONE: the gradients of the LSTM and FC parameters (97 % of the 75.5 MB)
+ *                         are enqueued, the conv-stack backward follows - the point where their all-reduce can start. */
+typedef int (*vs_stat_allreduce_fn)(void* user, double* device_sums, int32_t count, void* stream);
+typedef int (*vs_backward_hook_fn)(void* user, int32_t stage, void* stream);
+#define VS_BWD_STAGE_LSTM_FC_DONE 1
+int vs_engine_set_sync_bn(vs_engine* e, vs_stat_allreduce_fn fn, void* user, int32_t world_size);
+int vs_engine_set_backward_hook(vs_engine* e, vs_backward_hook_fn fn, void* user);
 size_t vs_train_workspace_bytes(const vs_engine* e, int32_t B, int32_t T);
 int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, const float* emb, float* mask,
                      int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_emb [B][E] and grad_x [B][T][F] (d loss / d spectrogram, through cnn1) are optional outputs (NULL = not wanted). */
 int vs_train_backward(vs_engine* e, const float* x, const float* emb, const float* mask, const float* grad_mask,
-                      const vs_grads* grads, float* grad_emb, int32_t B, int32_t T, void* workspace,
+                      const vs_grads* grads, float* grad_emb, float* grad_x, int32_t B, int32_t T, void* workspace,
                       size_t workspace_bytes, void* stream);
 
 /* ---- audio front / back end (BASELINE config 5) --------------------------

@@ -88,7 +88,7 @@ def test_cabi_exports_every_declared_symbol():
     lib = _cabi.load()     # loads without a GPU (static cudart, driver entry points resolved lazily)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vs_abi_version() == 1
+    assert lib.vs_abi_version() == 2
 
 
 def test_cabi_create_fails_loudly_without_gpu():

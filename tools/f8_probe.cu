@@ -23,18 +23,7 @@
 using namespace vs;
 using namespace vs::ptx;
 
-// kind::f8f6f4 instruction descriptor: a_format / b_format 0 = E4M3 (1 = E5M2), fp32 D, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+#define make_idesc_f8 make_idesc_e4m3   // shared with the product kernels (sm100_ptx.cuh)
 
 struct F8Args {
     const uint8_t* A8;    // [128][K] e4m3

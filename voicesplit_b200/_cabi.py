@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libvoicesplit_sm100.so")
 
 VS_OK = 0
 ACT_MISH, ACT_RELU = 0, 1
-PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3, PREC_FP16 = 0, 1, 2, 3, 4
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3, "fp16": PREC_FP16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3, PREC_FP16, PREC_FP16_F8C = 0, 1, 2, 3, 4, 5
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3, "fp16": PREC_FP16,
+              "fp16_f8c": PREC_FP16_F8C}
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -63,6 +64,10 @@ class VsGrads(ctypes.Structure):
 
 # name -> (restype, argtypes); must list every function include/voicesplit_b200.h declares
 _VP, _I, _SZ = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
+# data-parallel callbacks (vs_stat_allreduce_fn, vs_backward_hook_fn)
+STAT_ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _VP, _VP, _I, _VP)
+BACKWARD_HOOK_FN = ctypes.CFUNCTYPE(ctypes.c_int, _VP, _I, _VP)
+BWD_STAGE_LSTM_FC_DONE = 1
 SIGNATURES = {
     "vs_abi_version": (ctypes.c_int, []),
     "vs_last_error": (ctypes.c_char_p, []),
@@ -77,7 +82,9 @@ SIGNATURES = {
     "vs_engine_set_train_tensor_cores": (ctypes.c_int, [_VP, _I]),
     "vs_train_workspace_bytes": (_SZ, [_VP, _I, _I]),
     "vs_train_forward": (ctypes.c_int, [_VP, ctypes.POINTER(VsTrainState), _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),
-    "vs_train_backward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, ctypes.POINTER(VsGrads), _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_train_backward": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, ctypes.POINTER(VsGrads), _VP, _VP, _I, _I, _VP, _SZ, _VP]),
+    "vs_engine_set_sync_bn": (ctypes.c_int, [_VP, STAT_ALLREDUCE_FN, _VP, _I]),
+    "vs_engine_set_backward_hook": (ctypes.c_int, [_VP, BACKWARD_HOOK_FN, _VP]),
     "vs_audio_configure": (ctypes.c_int, [_VP, ctypes.POINTER(VsAudioParams), _VP]),
     "vs_audio_workspace_bytes": (_SZ, [_VP, _I, _I]),
     "vs_wav2spec": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),

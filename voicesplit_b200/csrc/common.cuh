@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -65,6 +66,27 @@ __device__ __forceinline__ void split16(float y, elt16& hi, elt16& lo) {
 __device__ __forceinline__ void split16_rt(float y, int elt, elt16& hi, elt16& lo) {
     if (elt == 0) split16<0>(y, hi, lo); else split16<1>(y, hi, lo);
 }
+// ---- VS_PREC_FP16_F8C: the fp8 correction plane ("c8") --------------------------------------------
+// An activation x is kept as hi = fp16(x) (the operand of the kind::f16 main pass) plus 128 bytes per pixel of e4m3
+// correction operands, channels innermost:   [ l8 = e4m3(2^8 * (x - hi)) x 64 | x8 = e4m3(2^-2 * hi) x 64 ].
+// Weights carry the matching row   [ e4m3(2^-8 * w_hi) x 64 | e4m3(2^2 * w_lo) x 64 ],   so ONE kind::f8f6f4 product over the
+// 128-byte K axis is  x_lo * w_hi + x_hi * w_lo  - the two correction terms of the split product - with the power-of-two
+// scales cancelling inside each product (the fp32 TMEM accumulator is shared with the unscaled main pass).
+constexpr float kF8cLoScale = 256.f, kF8cHiScale = 0.25f;
+__device__ __forceinline__ unsigned short e4m3x2(float a, float b) {   // low byte = e4m3(a), high byte = e4m3(b), saturating
+    return (unsigned short)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float e4m3_to_float(unsigned int byte) {
+    __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)(byte & 0xffu), __NV_E4M3);
+    return __half2float(*reinterpret_cast<__half*>(&h));
+}
+// hi (fp16 bits) and the float residual of y
+__device__ __forceinline__ void split_f8c(float y, elt16& hi, float& lo) {
+    y = fminf(fmaxf(y, -60000.f), 60000.f);
+    const __half h = __float2half_rn(y);
+    hi = __half_as_ushort(h);
+    lo = y - __half2float(h);
+}
 __device__ __forceinline__ float join16(elt16 hi, elt16 lo, int elt) {
     return elt == 0 ? __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo))
                     : __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
@@ -109,6 +131,12 @@ struct vs_engine {
     float* bn_gamma[8] = {};
     float* bn_beta[8] = {};
     float* ones64 = nullptr, *zeros64 = nullptr;
+    // data-parallel hooks (train.cu): SyncBN statistics all-reduce and the mid-backward notification
+    vs_stat_allreduce_fn sync_fn = nullptr;
+    void* sync_user = nullptr;
+    int sync_world = 1;
+    vs_backward_hook_fn bwd_hook = nullptr;
+    void* bwd_hook_user = nullptr;
     bool train_tc = true;       // training: forward and data-gradient convs on the tcgen05 conv kernel (else fp32 CUDA cores)
 
     // host staging for vs_forward_host (grow-only)

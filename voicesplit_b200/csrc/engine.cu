@@ -127,7 +127,7 @@ static int check_common(const vs_engine* e, int B, int T, int precision) {
     if (!e) { set_error("null engine"); return VS_ERR_INVALID; }
     if (!e->loaded) { set_error("parameters not loaded: call vs_engine_load_params first"); return VS_ERR_STATE; }
     if (B < 1 || T < 1) { set_error("B and T must be >= 1"); return VS_ERR_INVALID; }
-    if (precision < VS_PREC_FP32 || precision > VS_PREC_FP16) {
+    if (precision < VS_PREC_FP32 || precision > VS_PREC_FP16_F8C) {
         set_error("unknown precision"); return VS_ERR_INVALID;
     }
     // the kernels' tile schedulers keep tile and row indices in 32 bits

@@ -105,6 +105,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with e4m3 operands (kind::f8f6f4, K = 32 per instruction: twice the kind::f16 rate); may accumulate into a TMEM
+// tile that kind::f16 MMAs also accumulate into (verified on hardware: tools/f8_probe.cu, profiles/r01_f8_probe.txt)
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -142,6 +152,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int fp16 = 
            | (0u << 15) | (0u << 16)      // a_major = b_major = K
            | ((uint32_t)(N >> 3) << 17)   // n_dim
            | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+// Instruction descriptor for kind::f8f6f4 with e4m3 A/B (format code 0; e5m2 would be 1), both K-major, fp32 D.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // Shared-memory matrix descriptor.  layout: 0 = no swizzle (interleaved 8x16B core matrices),
 // 2 = 128B swizzle.  Offsets in bytes.  version = 1 (sm_100).

@@ -5,8 +5,13 @@
 namespace vs {
 
 // precision -> (number of MMA passes, 16-bit element type: 0 = bf16, 1 = fp16)
-inline int tc_passes(int precision) { return (precision == VS_PREC_BF16X3 || precision == VS_PREC_FP16X3) ? 3 : 1; }
-inline int tc_elt(int precision) { return (precision == VS_PREC_FP16X3 || precision == VS_PREC_FP16) ? 1 : 0; }
+// FP16_F8C keeps two operand planes like the x3 modes (fp16 hi + the e4m3 correction plane, common.cuh), so it reports "3":
+// every buffer is sized as for FP16X3; the conv kernels then issue 4 f16 + 4 f8f6f4 MMAs per tap pair instead of 12 f16.
+inline int tc_passes(int precision) { return (precision == VS_PREC_BF16X3 || precision == VS_PREC_FP16X3 || precision == VS_PREC_FP16_F8C) ? 3 : 1; }
+inline int tc_elt(int precision) { return (precision == VS_PREC_FP16X3 || precision == VS_PREC_FP16 || precision == VS_PREC_FP16_F8C) ? 1 : 0; }
+inline bool tc_f8c(int precision) { return precision == VS_PREC_FP16_F8C; }
+// arithmetic of the LSTM input projection / recurrence / FC head under each conv precision
+inline int tc_head_precision(int precision) { return precision == VS_PREC_FP16_F8C ? VS_PREC_FP16X3 : precision; }
 
 struct TcLstmBuffers {  // recurrent-kernel buffers shared with the fp32 path (carved by engine.cu)
     float* gates;       // [B*T][8H]
@@ -95,7 +100,7 @@ void tc_gemm_destroy(vs_engine* e);
 size_t tc_gemm_workspace_bytes(const vs_engine* e, int B, int T, int precision);
 // Everything after the 64-channel conv planes: cnn8 (+reshape), LSTM, head.  If conv_out32 is given
 // the planes are ignored and the LSTM input is taken from it (debug hook).
-int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32,
+int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, bool plane_f8c, const float* conv_out32,
                  const float* emb, const float* x, float* mask, float* masked, int B, int T, int precision, void* gemm_ws,
                  const TcLstmBuffers& lb, cudaStream_t st);
 // training (train.cu): raw forward conv / data-gradient conv of layer 1..6 on k_conv_tc, 3 passes, fp32 output plane
@@ -115,7 +120,7 @@ int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* ho
 void* tc_lstm_slot(vs_engine* e);  // LstmState pointer kept in TcState (tc_conv.cu)
 int tc_lstm_read_timing(void* slot, long long* out8);
 
-cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
+cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, bool f8c, float* x32, elt16* xhi,
                              elt16* xlo, int ldx, int B, int T, cudaStream_t st);
 
 }  // namespace vs

@@ -25,6 +25,7 @@
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace vs {
 using namespace ptx;
@@ -40,7 +41,8 @@ struct ConvTcArgs {
     int tiles_per_utt, total_tiles;
     int n_dt, n_j, halo;  // taps along T, tap pairs along F, strip halo (2 for 5x5, 0 for 7x1)
     int dt_stride;        // dilation * Fp: flat-pixel offset of one tap step along T
-    int passes;           // 1 (bf16) or 3 (bf16x3)
+    int passes;           // 1 (single 16-bit pass) or 3 (two operand planes: hi/lo split, or hi + fp8 correction plane)
+    int f8c;              // VS_PREC_FP16_F8C: second plane = e4m3 correction operands, 4 f16 + 4 f8f6f4 MMAs per tap pair
     int strip_rows, box_rows, n_boxes, s_stages;
     int act;
     const float* scale;
@@ -57,7 +59,7 @@ __device__ __forceinline__ float act_fast(float x) {
     return mish_f(x);
 }
 
-template <int ACT, int ELT, bool OUT32>
+template <int ACT, int ELT, bool OUT32, bool F8C>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
                                                     const __grid_constant__ CUtensorMap tm_w_hi,
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
         if (lane == 0) {
             // ===================== MMA issuer =====================
             const uint32_t idesc = make_idesc_bf16(128, a.N, ELT);
+            const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
             int ws = 0, wph = 0, ss = 0, sph = 0, it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1, aph = (it >> 1) & 1;
@@ -160,14 +163,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                             mbar_wait(&w_full[ws], wph);
                             tc_fence_after();
                             const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWTileBytes);
-                            const int n_sp = (wp == 0) ? n_strip_loads : 1;
-                            for (int sp = 0; sp < n_sp; ++sp) {
-                                const uint32_t b_addr = s_addr[sp] + (uint32_t)(2 * j) * 128;
+                            if (F8C) {
+                                // wp 0: W_hi x S_hi as four kind::f16 MMAs (K = 16); wp 1: the e4m3 correction tile x the c8 strip as
+                                // four kind::f8f6f4 MMAs (K = 32 bytes each): x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
+                                const uint32_t b_addr = s_addr[wp] + (uint32_t)(2 * j) * 128;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
-                                              idesc, accumulate);
+                                    if (wp == 0)
+                                        umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
+                                                  idesc, accumulate);
+                                    else
+                                        umma_f8(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
+                                                idesc8, 1);
                                     accumulate = 1;
+                                }
+                            } else {
+                                const int n_sp = (wp == 0) ? n_strip_loads : 1;
+                                for (int sp = 0; sp < n_sp; ++sp) {
+                                    const uint32_t b_addr = s_addr[sp] + (uint32_t)(2 * j) * 128;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
+                                                  idesc, accumulate);
+                                        accumulate = 1;
+                                    }
                                 }
                             }
                             umma_commit(&w_empty[ws]);
@@ -195,8 +214,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
             int f = (q0 + h + cgrp * 32) % a.Fp;         // frequency index of this lane's first pixel
-            elt16* ohi = OUT32 ? nullptr : a.out_hi + ((size_t)b * a.Q + q0) * 64 + co;
-            elt16* olo = (!OUT32 && want_lo) ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
+            // 16-bit outputs: lanes L and L^2 hold channels co, co^1 of the same pixels; they swap every other value so that
+            // each lane stores a CHANNEL PAIR (4 bytes per plane) of every second pixel instead of 2 bytes of every pixel
+            const int codd = (lane >> 1) & 1;
+            elt16* ohi = OUT32 ? nullptr : a.out_hi + ((size_t)b * a.Q + q0) * 64 + (co & ~1);
+            elt16* olo = (!OUT32 && want_lo) ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + (co & ~1) : nullptr;
+            uint8_t* oc8 = (!OUT32 && F8C) ? reinterpret_cast<uint8_t*>(a.out_lo) + ((size_t)b * a.Q + q0) * 128 + (co & ~1) : nullptr;
             float* o32 = OUT32 ? a.out32 + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
             for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (kEpiWarps / 4)) {
                 uint32_t r[32];
@@ -206,26 +229,49 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(nxt) : "r"(t_base + c0 + 32) : "memory");
                 tmem_ld_wait();
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    // even lane (h=0, lower tap) owns pixel c0+2m, odd lane (upper tap) pixel c0+2m+1
-                    const float mine_odd = __uint_as_float(r[2 * m + 1]);
-                    const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
-                    const float up_next = __uint_as_float(m < 15 ? r[(2 * m + 2) & 31] : nxt);
-                    const float acc = h == 0 ? __uint_as_float(r[2 * m]) + other_odd : other_odd + up_next;
-                    const int p = c0 + 2 * m + h;
-                    if (p < useful && q0 + p < a.Q) {
-                        float y = (f < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
-                        if (OUT32) {
-                            o32[(size_t)p * 64] = y;
-                        } else {
-                            elt16 yh, yl;
-                            split16<ELT>(y, yh, yl);
-                            ohi[(size_t)p * 64] = yh;
-                            if (want_lo) olo[(size_t)p * 64] = yl;
+                for (int m = 0; m < 16; m += 2) {
+                    float y[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        // even lane (h=0, lower tap) owns pixel c0+2(m+i), odd lane (upper tap) pixel c0+2(m+i)+1
+                        const int mm = m + i;
+                        const float mine_odd = __uint_as_float(r[2 * mm + 1]);
+                        const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
+                        const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
+                        const float acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
+                        y[i] = (f < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
+                        f += 2;
+                        if (f >= a.Fp) f -= a.Fp;
+                    }
+                    if (OUT32) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int p = c0 + 2 * (m + i) + h;
+                            if (p < useful && q0 + p < a.Q) o32[(size_t)p * 64] = y[i];
+                        }
+                    } else {
+                        // channel-even lane keeps the first pixel, channel-odd lane the second; each receives the partner channel
+                        const float recv = __shfl_xor_sync(0xffffffffu, codd ? y[0] : y[1], 2);
+                        const float v0 = codd ? recv : y[0], v1 = codd ? y[1] : recv;      // channels (co & ~1), (co | 1)
+                        const int p = c0 + 2 * (m + codd) + h;
+                        if (p < useful && q0 + p < a.Q) {
+                            if (F8C) {
+                                elt16 h0, h1;
+                                float l0, l1;
+                                split_f8c(v0, h0, l0);
+                                split_f8c(v1, h1, l1);
+                                *reinterpret_cast<uint32_t*>(ohi + (size_t)p * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                *reinterpret_cast<unsigned short*>(oc8 + (size_t)p * 128) = e4m3x2(kF8cLoScale * l0, kF8cLoScale * l1);
+                                *reinterpret_cast<unsigned short*>(oc8 + (size_t)p * 128 + 64) = e4m3x2(kF8cHiScale * v0, kF8cHiScale * v1);
+                            } else {
+                                elt16 h0, l0, h1, l1;
+                                split16<ELT>(v0, h0, l0);
+                                split16<ELT>(v1, h1, l1);
+                                *reinterpret_cast<uint32_t*>(ohi + (size_t)p * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                if (want_lo) *reinterpret_cast<uint32_t*>(olo + (size_t)p * 64) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                            }
                         }
                     }
-                    f += 2;
-                    if (f >= a.Fp) f -= a.Fp;
                 }
                 f = (f + 32 * (kEpiWarps / 4 - 1)) % a.Fp;   // skip the chunks the other warps take
             }
@@ -242,7 +288,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
 // ---------------------------------------------------------------------------------------------
 // cnn1 on CUDA cores, writing the bf16 hi/lo planes (K = 7, C_in = 1: not MMA-shaped)
 // ---------------------------------------------------------------------------------------------
-template <int ACT, int ELT>
+template <int ACT, int ELT, bool F8C>
 __global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x, elt16* __restrict__ hi,
                                                      elt16* __restrict__ lo, const float* __restrict__ w,
                                                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -275,17 +321,26 @@ __global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x
             for (int p = 0; p < 2; ++p) {
                 const int f = f0 + p;
                 __align__(8) elt16 vh[4], vl[4];
+                float yv[4], rl[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc = fmaf(wr[j][c], xv[p + j], acc);
-                    float y = (f < F) ? act_fast<ACT>(fmaf(acc, sc[c], sh[c])) : 0.f;
-                    split16<ELT>(y, vh[c], vl[c]);
+                    yv[c] = (f < F) ? act_fast<ACT>(fmaf(acc, sc[c], sh[c])) : 0.f;
+                    if (F8C) split_f8c(yv[c], vh[c], rl[c]); else split16<ELT>(yv[c], vh[c], vl[c]);
                 }
                 const size_t o = ((size_t)row * Fp + f) * 64 + cg * 4;
                 *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(vh);
-                if (lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(vl);
+                if (F8C) {   // `lo` is the c8 plane: 128 bytes per pixel, [l8 x 64 | x8 x 64]
+                    uint8_t* c8 = reinterpret_cast<uint8_t*>(lo) + ((size_t)row * Fp + f) * 128 + cg * 4;
+                    *reinterpret_cast<uint32_t*>(c8) = (uint32_t)e4m3x2(kF8cLoScale * rl[0], kF8cLoScale * rl[1]) |
+                                                       ((uint32_t)e4m3x2(kF8cLoScale * rl[2], kF8cLoScale * rl[3]) << 16);
+                    *reinterpret_cast<uint32_t*>(c8 + 64) = (uint32_t)e4m3x2(kF8cHiScale * yv[0], kF8cHiScale * yv[1]) |
+                                                            ((uint32_t)e4m3x2(kF8cHiScale * yv[2], kF8cHiScale * yv[3]) << 16);
+                } else if (lo) {
+                    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(vl);
+                }
             }
         }
     }
@@ -295,7 +350,7 @@ __global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x
 // cnn8 (64 -> 8, 1x1) + BN + act from the bf16 planes; output row layout [B*T][ldx] with column
 // c*F+f, as fp32 and/or bf16 hi/lo (the LSTM input-projection operand)
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, bool F8C>
 __global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi, const elt16* __restrict__ lo, int elt,
                                                    const float* __restrict__ w, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, float* __restrict__ x32,
@@ -341,12 +396,17 @@ __global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi,
 #pragma unroll 2
     for (int q = 0; q < 8; ++q) {
         const uint4 vh = *reinterpret_cast<const uint4*>(s_hi + tid * 144 + q * 16);
-        const uint4 vl = lo ? *reinterpret_cast<const uint4*>(s_lo + tid * 144 + q * 16) : make_uint4(0, 0, 0, 0);
         const elt16* ph = reinterpret_cast<const elt16*>(&vh);
+        uint4 vl = make_uint4(0, 0, 0, 0);
+        uint2 v8 = make_uint2(0, 0);
+        if (F8C) v8 = *reinterpret_cast<const uint2*>(s_lo + tid * 144 + q * 8);   // l8 of channels 8q..8q+7 (first half of the c8 row)
+        else if (lo) vl = *reinterpret_cast<const uint4*>(s_lo + tid * 144 + q * 16);
         const elt16* pl = reinterpret_cast<const elt16*>(&vl);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float v = join16(ph[k], pl[k], elt);
+            const float v = F8C ? __half2float(__ushort_as_half(ph[k])) +
+                                      e4m3_to_float((k < 4 ? v8.x : v8.y) >> (8 * (k & 3))) * (1.f / kF8cLoScale)
+                                : join16(ph[k], pl[k], elt);
             const float4 w0 = *reinterpret_cast<const float4*>(ws + (q * 8 + k) * 8);
             const float4 w1 = *reinterpret_cast<const float4*>(ws + (q * 8 + k) * 8 + 4);
             acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
@@ -382,6 +442,26 @@ __global__ void k_plane_join(const elt16* __restrict__ hi, const elt16* __restri
     p[i] = join16(hi[i], lo ? lo[i] : (elt16)0, elt);
 }
 
+// the same for the hi + c8 plane pair of VS_PREC_FP16_F8C (the join reads what a consumer of the values sees: hi + 2^-8 l8)
+__global__ void k_plane_split_f8c(const float* __restrict__ p, elt16* __restrict__ hi, uint8_t* __restrict__ c8, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    elt16 h;
+    float l;
+    split_f8c(p[i], h, l);
+    hi[i] = h;
+    const unsigned short pr = e4m3x2(kF8cLoScale * l, kF8cHiScale * p[i]);
+    const long long px = i >> 6;
+    const int ch = (int)(i & 63);
+    c8[px * 128 + ch] = (uint8_t)(pr & 0xff);
+    c8[px * 128 + 64 + ch] = (uint8_t)(pr >> 8);
+}
+__global__ void k_plane_join_f8c(const elt16* __restrict__ hi, const uint8_t* __restrict__ c8, float* __restrict__ p, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p[i] = __half2float(__ushort_as_half(hi[i])) + e4m3_to_float(c8[(i >> 6) * 128 + (i & 63)]) * (1.f / kF8cLoScale);
+}
+
 // max |w| of a weight tensor (bits of a non-negative float order like unsigned ints)
 __global__ void k_absmax(const float* __restrict__ w, int n, unsigned int* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,6 +489,26 @@ __global__ void k_pack_conv_tc(const float* __restrict__ w32, const unsigned int
     split16<0>(v, bhi[i], blo[i]);
     split16<1>(v, hhi[i], hlo[i]);
 }
+// VS_PREC_FP16_F8C correction tiles, same [step][row = 2co+h] order, 128 bytes per row:
+// [ e4m3(2^-8 * w_hi)[ci] x 64 | e4m3(2^2 * w_lo)[ci] x 64 ]  with  w = s * weight = w_hi (fp16) + w_lo
+__global__ void k_pack_conv_f8c(const float* __restrict__ w32, const unsigned int* __restrict__ maxbits, uint8_t* __restrict__ w8, int kh, int kw,
+                                int n_j) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = kh * n_j * 128 * 64;
+    if (i >= n) return;
+    const float s = pow2_scale(*maxbits);
+    int ci = i & 63, row = (i >> 6) & 127, step = i >> 13;
+    int dt = step / n_j, j = step % n_j;
+    int co = row >> 1, h = row & 1, df = 2 * j + h;
+    float v = (df < kw) ? s * w32[((size_t)(dt * kw + df) * 64 + ci) * 64 + co] : 0.f;
+    elt16 hi;
+    float lo;
+    split_f8c(v, hi, lo);
+    const unsigned short pr = e4m3x2(__half2float(__ushort_as_half(hi)) * (1.f / kF8cLoScale), lo * (1.f / kF8cHiScale));
+    uint8_t* dst = w8 + ((size_t)step * 128 + row) * 128;
+    dst[ci] = (uint8_t)(pr & 0xff);
+    dst[64 + ci] = (uint8_t)(pr >> 8);
+}
 __global__ void k_scale_tc(const float* __restrict__ scale, const unsigned int* __restrict__ maxbits, float* __restrict__ out, int n) {
     int i = threadIdx.x;
     if (i < n) out[i] = scale[i] / pow2_scale(*maxbits);
@@ -423,6 +523,7 @@ struct TcState {
     elt16* w_hi[2][8] = {};   // [elt][layer]
     elt16* w_lo[2][8] = {};
     float* scale_tc[8] = {};  // BN scale divided by the layer's power-of-two weight scale
+    uint8_t* w_c8[8] = {};    // VS_PREC_FP16_F8C: e4m3 correction tiles (k_pack_conv_f8c)
     elt16* wT_hi[2][8] = {};  // training: data-gradient weights (taps flipped, channels transposed), same tile format
     elt16* wT_lo[2][8] = {};
     float* unscale[8] = {};   // 64 copies of 1 / (power-of-two weight scale): epilogue scale of the raw-output convs
@@ -445,7 +546,7 @@ void tc_destroy(vs_engine* e) {
     tc_lstm_destroy(s->lstm);
     for (int l = 0; l < 8; ++l) {
         for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); cudaFree(s->wT_hi[t][l]); cudaFree(s->wT_lo[t][l]); }
-        cudaFree(s->scale_tc[l]); cudaFree(s->unscale[l]);
+        cudaFree(s->scale_tc[l]); cudaFree(s->unscale[l]); cudaFree(s->w_c8[l]);
     }
     cudaFree(s->wmax);
     delete s;
@@ -467,6 +568,7 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
                 VS_CUDA_TRY(cudaMalloc(&s->wT_hi[t][l], n * sizeof(elt16)));
                 VS_CUDA_TRY(cudaMalloc(&s->wT_lo[t][l], n * sizeof(elt16)));
             }
+            VS_CUDA_TRY(cudaMalloc(&s->w_c8[l], n * 2));
             VS_CUDA_TRY(cudaMalloc(&s->scale_tc[l], 64 * sizeof(float)));
             VS_CUDA_TRY(cudaMalloc(&s->unscale[l], 64 * sizeof(float)));
         }
@@ -474,6 +576,7 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
         k_absmax<<<(nw + 255) / 256, 256, 0, st>>>(e->conv_w32[l], nw, s->wmax + l);
         k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_hi[0][l], s->w_lo[0][l],
                                                                     s->w_hi[1][l], s->w_lo[1][l], g.kh, g.kw, n_j);
+        k_pack_conv_f8c<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_c8[l], g.kh, g.kw, n_j);
         k_scale_tc<<<1, 64, 0, st>>>(e->conv_scale[l], s->wmax + l, s->scale_tc[l], 64);
         // training: the same power-of-two scale serves the flipped/transposed data-gradient weights (same values)
         k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_wT32[l], s->wmax + l, s->wT_hi[0][l], s->wT_lo[0][l],
@@ -493,6 +596,7 @@ struct ConvTcCall {            // what differs between the eval layers and the t
     int act;                   // VS_ACT_* or 2 (pass-through)
     float* out32;              // non-null: fp32 output plane
     int kid;
+    bool f8c = false;          // w_lo = e4m3 correction tiles, in_lo / out_lo = c8 planes
 };
 static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo, elt16* out_hi, elt16* out_lo, int B, int T,
                              int passes, int elt, const ConvTcCall& call, cudaStream_t st);
@@ -503,6 +607,7 @@ static int launch_conv_tc(vs_engine* e, int layer, const elt16* in_hi, const elt
     const int elt = tc_elt(precision);
     ConvTcCall call{s->w_hi[elt][layer], s->w_lo[elt][layer], s->scale_tc[layer], e->conv_shift[layer], e->d.activation, nullptr,
                     KID_CONV1 + layer - 1};
+    if (tc_f8c(precision)) { call.w_lo = reinterpret_cast<const elt16*>(s->w_c8[layer]); call.f8c = true; }
     return launch_conv_tc_ex(e, layer, in_hi, in_lo, out_hi, out_lo, B, T, tc_passes(precision), elt, call, st);
 }
 
@@ -528,6 +633,8 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     a.n_dt = g.kh; a.n_j = (g.kw + 1) / 2; a.halo = g.kw / 2;
     a.dt_stride = g.dil * Fp;
     a.passes = passes;
+    a.f8c = call.f8c ? 1 : 0;
+    if (call.f8c && (passes != 3 || !elt || call.out32 || !in_lo || !out_lo)) { set_error("fp16_f8c conv needs the fp16 hi + c8 plane pair"); return VS_ERR_INVALID; }
     a.strip_rows = a.N + 8;
     a.box_rows = a.strip_rows;
     a.n_boxes = 1;
@@ -563,16 +670,18 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     }
     int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
     cudaError_t ce;
-#define VS_CONV_TC(A, E, O)                                                                               \
-    do {                                                                                                  \
-        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-        if (ce == cudaSuccess) k_conv_tc<A, E, O><<<grid, kConvThreads, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+#define VS_CONV_TC(A, E, O, F8)                                                                               \
+    do {                                                                                                      \
+        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+        if (ce == cudaSuccess) k_conv_tc<A, E, O, F8><<<grid, kConvThreads, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
     if (call.out32) {
         if (call.act != 2) { set_error("fp32-output conv is pass-through only"); return VS_ERR_INVALID; }
-        if (elt) VS_CONV_TC(2, 1, true); else VS_CONV_TC(2, 0, true);
-    } else if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1, false); else VS_CONV_TC(VS_ACT_RELU, 0, false); }
-    else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1, false); else VS_CONV_TC(VS_ACT_MISH, 0, false); }
+        if (elt) VS_CONV_TC(2, 1, true, false); else VS_CONV_TC(2, 0, true, false);
+    } else if (call.f8c) {
+        if (a.act == VS_ACT_RELU) VS_CONV_TC(VS_ACT_RELU, 1, false, true); else VS_CONV_TC(VS_ACT_MISH, 1, false, true);
+    } else if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1, false, false); else VS_CONV_TC(VS_ACT_RELU, 0, false, false); }
+    else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1, false, false); else VS_CONV_TC(VS_ACT_MISH, 0, false, false); }
 #undef VS_CONV_TC
     if (ce == cudaSuccess) ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_error(std::string("k_conv_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
@@ -581,35 +690,39 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     return VS_OK;
 }
 
-static cudaError_t launch_front_tc(const vs_engine* e, const float* x, elt16* hi, elt16* lo, int elt, int B, int T, cudaStream_t st) {
+static cudaError_t launch_front_tc(const vs_engine* e, const float* x, elt16* hi, elt16* lo, int elt, bool f8c, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
     const int nrows = B * T;
     const int grid = nrows < e->num_sms * 12 ? nrows : e->num_sms * 12;
     const size_t smem = (size_t)(Fp + 8) * sizeof(float);
-#define VS_FRONT(A, E) k_front_tc<A, E><<<grid, 256, smem, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], F, Fp, nrows)
-    if (e->d.activation == VS_ACT_RELU) { if (elt) VS_FRONT(VS_ACT_RELU, 1); else VS_FRONT(VS_ACT_RELU, 0); }
-    else { if (elt) VS_FRONT(VS_ACT_MISH, 1); else VS_FRONT(VS_ACT_MISH, 0); }
+#define VS_FRONT(A, E, F8) k_front_tc<A, E, F8><<<grid, 256, smem, st>>>(x, hi, lo, e->conv_w32[0], e->conv_scale[0], e->conv_shift[0], F, Fp, nrows)
+    if (f8c) { if (e->d.activation == VS_ACT_RELU) VS_FRONT(VS_ACT_RELU, 1, true); else VS_FRONT(VS_ACT_MISH, 1, true); }
+    else if (e->d.activation == VS_ACT_RELU) { if (elt) VS_FRONT(VS_ACT_RELU, 1, false); else VS_FRONT(VS_ACT_RELU, 0, false); }
+    else { if (elt) VS_FRONT(VS_ACT_MISH, 1, false); else VS_FRONT(VS_ACT_MISH, 0, false); }
 #undef VS_FRONT
     return cudaGetLastError();
 }
 
-static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32,
+template <int ACT, bool F8C>
+static cudaError_t launch_point8_one(const vs_engine* e, unsigned grid, int smem, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
+                                     elt16* xlo, int ldx, int F, int Fp, long long nplane, cudaStream_t st) {
+    cudaError_t ce = cudaFuncSetAttribute(k_point8_tc<ACT, F8C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) return ce;
+    k_point8_tc<ACT, F8C><<<grid, 256, smem, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, nplane);
+    return cudaGetLastError();
+}
+// f8c: `lo` is the c8 correction plane of VS_PREC_FP16_F8C (the value is hi + 2^-8 * l8)
+static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, bool f8c, float* x32,
                                     elt16* xhi, elt16* xlo, int ldx, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
     const long long nplane = (long long)B * T * Fp;
     const unsigned grid = (unsigned)((nplane + 255) / 256);
     const int smem = 2 * 256 * 144;
-    cudaError_t ce;
-    if (e->d.activation == VS_ACT_RELU) {
-        ce = cudaFuncSetAttribute(k_point8_tc<VS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (ce != cudaSuccess) return ce;
-        k_point8_tc<VS_ACT_RELU><<<grid, 256, smem, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, nplane);
-    } else {
-        ce = cudaFuncSetAttribute(k_point8_tc<VS_ACT_MISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (ce != cudaSuccess) return ce;
-        k_point8_tc<VS_ACT_MISH><<<grid, 256, smem, st>>>(hi, lo, elt, e->conv_w32[7], e->conv_scale[7], e->conv_shift[7], x32, xhi, xlo, ldx, F, Fp, nplane);
-    }
-    return cudaGetLastError();
+    const bool relu = e->d.activation == VS_ACT_RELU;
+    if (f8c) return relu ? launch_point8_one<VS_ACT_RELU, true>(e, grid, smem, hi, lo, elt, x32, xhi, xlo, ldx, F, Fp, nplane, st)
+                         : launch_point8_one<VS_ACT_MISH, true>(e, grid, smem, hi, lo, elt, x32, xhi, xlo, ldx, F, Fp, nplane, st);
+    return relu ? launch_point8_one<VS_ACT_RELU, false>(e, grid, smem, hi, lo, elt, x32, xhi, xlo, ldx, F, Fp, nplane, st)
+                : launch_point8_one<VS_ACT_MISH, false>(e, grid, smem, hi, lo, elt, x32, xhi, xlo, ldx, F, Fp, nplane, st);
 }
 
 // ---- workspace of the tensor-core path ---------------------------------------------------------
@@ -640,7 +753,7 @@ size_t tc_workspace_bytes(const vs_engine* e, int B, int T, int precision) { ret
 // conv stack on tensor cores; result in the bf16 plane pair returned through (*res_hi, *res_lo)
 static int conv_layers_tc(vs_engine* e, const float* x, const TcWorkspace& w, int B, int T, int precision, cudaStream_t st,
                           elt16** res_hi, elt16** res_lo) {
-    VS_LAUNCH(e, KID_FRONT, st, launch_front_tc(e, x, w.a_hi, w.a_lo, tc_elt(precision), B, T, st));
+    VS_LAUNCH(e, KID_FRONT, st, launch_front_tc(e, x, w.a_hi, w.a_lo, tc_elt(precision), tc_f8c(precision), B, T, st));
     elt16 *sh = w.a_hi, *sl = w.a_lo, *dh = w.b_hi, *dl = w.b_lo;
     for (int l = 1; l <= 6; ++l) {
         int rc = launch_conv_tc(e, l, sh, sl, dh, dl, B, T, precision, st);
@@ -658,7 +771,7 @@ int tc_conv_stack(vs_engine* e, const float* x, float* conv_out, int B, int T, i
     elt16 *rh, *rl;
     int rc = conv_layers_tc(e, x, w, B, T, precision, st, &rh, &rl);
     if (rc != VS_OK) return rc;
-    VS_LAUNCH(e, KID_POINT8, st, launch_point8_tc(e, rh, rl, tc_elt(precision), conv_out, nullptr, nullptr, 8 * e->d.num_freq, B, T, st));
+    VS_LAUNCH(e, KID_POINT8, st, launch_point8_tc(e, rh, rl, tc_elt(precision), tc_f8c(precision), conv_out, nullptr, nullptr, 8 * e->d.num_freq, B, T, st));
     return VS_OK;
 }
 
@@ -668,7 +781,7 @@ int tc_forward(vs_engine* e, const float* x, const float* emb, float* mask, floa
     elt16 *rh, *rl;
     int rc = conv_layers_tc(e, x, w, B, T, precision, st, &rh, &rl);
     if (rc != VS_OK) return rc;
-    return tc_lstm_head(e, rh, rl, nullptr, emb, x, mask, masked, B, T, precision, w.gemm, lb, st);
+    return tc_lstm_head(e, rh, rl, tc_f8c(precision), nullptr, emb, x, mask, masked, B, T, tc_head_precision(precision), w.gemm, lb, st);
 }
 
 int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_in, float* plane_out, int B, int T,
@@ -682,14 +795,17 @@ int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_i
     const int elt = tc_elt(precision);
     int rc = VS_OK;
     cudaError_t ce = cudaSuccess;
+    const bool f8c = tc_f8c(precision);
     if (layer == 0) {
-        ce = launch_front_tc(e, x, oh, x3 ? ol : nullptr, elt, B, T, st);
+        ce = launch_front_tc(e, x, oh, x3 ? ol : nullptr, elt, f8c, B, T, st);
     } else {
-        k_plane_split<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(plane_in, ih, x3 ? il : nullptr, elt, n);
+        if (f8c) k_plane_split_f8c<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(plane_in, ih, reinterpret_cast<uint8_t*>(il), n);
+        else k_plane_split<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(plane_in, ih, x3 ? il : nullptr, elt, n);
         rc = launch_conv_tc(e, layer, ih, x3 ? il : nullptr, oh, ol, B, T, precision, st);
     }
     if (rc == VS_OK && ce == cudaSuccess) {
-        k_plane_join<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, x3 ? ol : nullptr, elt, plane_out, n);
+        if (f8c) k_plane_join_f8c<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, reinterpret_cast<const uint8_t*>(ol), plane_out, n);
+        else k_plane_join<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, x3 ? ol : nullptr, elt, plane_out, n);
         ce = cudaStreamSynchronize(st);
     }
     cudaFree(buf);
@@ -697,9 +813,9 @@ int tc_debug_layer(vs_engine* e, int layer, const float* x, const float* plane_i
     return rc;
 }
 
-cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, float* x32, elt16* xhi,
+cudaError_t tc_launch_point8(const vs_engine* e, const elt16* hi, const elt16* lo, int elt, bool f8c, float* x32, elt16* xhi,
                              elt16* xlo, int ldx, int B, int T, cudaStream_t st) {
-    return launch_point8_tc(e, hi, lo, elt, x32, xhi, xlo, ldx, B, T, st);
+    return launch_point8_tc(e, hi, lo, elt, f8c, x32, xhi, xlo, ldx, B, T, st);
 }
 
 }  // namespace vs

@@ -470,7 +470,7 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     return VS_OK;
 }
 
-int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, const float* conv_out32, const float* emb,
+int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, bool plane_f8c, const float* conv_out32, const float* emb,
                  const float* x, float* mask, float* masked, int B, int T, int precision, void* gemm_ws,
                  const TcLstmBuffers& lb, cudaStream_t st) {
     GemmState* g = g_state(e);
@@ -483,7 +483,7 @@ int tc_lstm_head(vs_engine* e, const elt16* plane_hi, const elt16* plane_lo, con
         k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(conv_out32, n, elt, w.x_hi, w.x_lo);
         VS_LAUNCH(e, KID_CONVERT, st, cudaGetLastError());
     } else {
-        VS_LAUNCH(e, KID_POINT8, st, tc_launch_point8(e, plane_hi, plane_lo, elt, nullptr, w.x_hi, w.x_lo, 8 * F, B, T, st));
+        VS_LAUNCH(e, KID_POINT8, st, tc_launch_point8(e, plane_hi, plane_lo, elt, plane_f8c, nullptr, w.x_hi, w.x_lo, 8 * F, B, T, st));
     }
     // d-vector folded into a per-utterance gate bias (tiny: B x 8H x E, fp32 FFMA)
     VS_LAUNCH(e, KID_EMB_BIAS, st, launch_gemm_fp32(emb, E, e->wih_e, E, e->b_lstm, nullptr, 1, lb.bias_u, 8 * H, B, 8 * H, E,
@@ -580,7 +580,8 @@ int tc_debug_lstm_head(vs_engine* e, const float* conv_out, const float* emb, co
                        int precision, const TcLstmBuffers& lb, cudaStream_t st) {
     void* ws = nullptr;
     VS_CUDA_TRY(cudaMalloc(&ws, tc_gemm_workspace_bytes(e, B, T, precision)));
-    int rc = tc_lstm_head(e, nullptr, nullptr, conv_out, emb, x, mask, nullptr, B, T, precision, ws, lb, st);
+    precision = tc_head_precision(precision);
+    int rc = tc_lstm_head(e, nullptr, nullptr, false, conv_out, emb, x, mask, nullptr, B, T, precision, ws, lb, st);
     cudaStreamSynchronize(st);
     cudaFree(ws);
     return rc;

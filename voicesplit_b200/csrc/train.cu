@@ -8,10 +8,6 @@
 
 namespace vs {
 
-__global__ void k_sums_to_grads(const double* __restrict__ sums, float* dgamma, float* dbeta, int C) {
-    int c = threadIdx.x;
-    if (c < C) { if (dbeta) dbeta[c] = (float)sums[c]; if (dgamma) dgamma[c] = (float)sums[64 + c]; }
-}
 __global__ void k_sum0_to_float(const double* __restrict__ sums, float* out, int C) {
     int c = threadIdx.x;
     if (c < C && out) out[c] = (float)sums[c];
@@ -98,6 +94,18 @@ using namespace vs;
 
 extern "C" {
 
+int vs_engine_set_sync_bn(vs_engine* e, vs_stat_allreduce_fn fn, void* user, int32_t world_size) {
+    if (!e) { set_error("null engine"); return VS_ERR_INVALID; }
+    if (fn && world_size < 1) { set_error("world_size must be >= 1"); return VS_ERR_INVALID; }
+    e->sync_fn = fn; e->sync_user = user; e->sync_world = fn ? world_size : 1;
+    return VS_OK;
+}
+int vs_engine_set_backward_hook(vs_engine* e, vs_backward_hook_fn fn, void* user) {
+    if (!e) { set_error("null engine"); return VS_ERR_INVALID; }
+    e->bwd_hook = fn; e->bwd_hook_user = user;
+    return VS_OK;
+}
+
 int vs_engine_set_train_tensor_cores(vs_engine* e, int32_t enabled) {
     if (!e) { set_error("null engine"); return VS_ERR_INVALID; }
     e->train_tc = enabled != 0;
@@ -119,6 +127,7 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
     const int F = e->d.num_freq, H = e->d.lstm_dim, E = e->d.emb_dim, N1 = e->d.fc1_dim, Fp = padded_freq(F), act = e->d.activation;
     const long long M = (long long)B * T;
     const float mom = bn ? bn->momentum : 0.1f;
+    const BnSync sync = bn_sync_of(e);
     e->launches = 0;
     prof_begin(e, st);
     // conv stack with batch statistics: z_l = conv(a_{l-1}) + bias, a_l = act(BN_batch(z_l))
@@ -132,7 +141,8 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
             TRK(e, KID_TR_CONV_FWD, st, launch_conv_fp32_ex(e, l, w.P, w.z[l], e->conv_w32[l], e->ones64, e->conv_bias[l], VS_ACT_NONE, B, T, st));
         }
         TRK(e, KID_TR_BN_STATS, st, tr_bn_stats_plane(w.z[l], w.sums, F, Fp, M, e->num_sms, st));
-        TR(e, st, tr_bn_finalize(w.sums, (double)M * F, e->bn_gamma[l], e->bn_beta[l], w.stat + l * 256, bn ? bn->running_mean[l] : nullptr,
+        if (sync.fn) TR(e, st, tr_bn_sync(sync, w.sums, st));
+        TR(e, st, tr_bn_finalize(w.sums, (double)M * F * sync.world, e->bn_gamma[l], e->bn_beta[l], w.stat + l * 256, bn ? bn->running_mean[l] : nullptr,
                                  bn ? bn->running_var[l] : nullptr, bn ? (long long*)bn->num_batches_tracked[l] : nullptr, mom, 64, st));
         const bool tc_next = e->train_tc && l < 6;     // the next layer's conv reads the 16-bit planes
         TRK(e, KID_TR_BN_ACT, st, tr_bn_act_plane(act, w.z[l], tc_next ? nullptr : w.P, w.stat + l * 256, F, Fp, M * Fp, st,
@@ -140,7 +150,8 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
     }
     TR(e, st, launch_point8_fp32_ex(e, w.P, w.z7, e->conv_w32[7], e->ones64, e->conv_bias[7], VS_ACT_NONE, B, T, st));
     TR(e, st, tr_bn_stats_cols(w.z7, w.sums, 8, F, M, e->num_sms, st));
-    TR(e, st, tr_bn_finalize(w.sums, (double)M * F, e->bn_gamma[7], e->bn_beta[7], w.stat + 7 * 256, bn ? bn->running_mean[7] : nullptr,
+    if (sync.fn) TR(e, st, tr_bn_sync(sync, w.sums, st));
+    TR(e, st, tr_bn_finalize(w.sums, (double)M * F * sync.world, e->bn_gamma[7], e->bn_beta[7], w.stat + 7 * 256, bn ? bn->running_mean[7] : nullptr,
                              bn ? bn->running_var[7] : nullptr, bn ? (long long*)bn->num_batches_tracked[7] : nullptr, mom, 8, st));
     TR(e, st, tr_bn_act_cols(act, w.z7, w.xcat, w.stat + 7 * 256, 8, F, M, st));
     // BiLSTM (gate activations and cell states are kept for the backward) and head
@@ -158,7 +169,7 @@ int vs_train_forward(vs_engine* e, const vs_train_state* bn, const float* x, con
 }
 
 int vs_train_backward(vs_engine* e, const float* x, const float* emb, const float* mask, const float* grad_mask, const vs_grads* g,
-                      float* grad_emb, int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream) {
+                      float* grad_emb, float* grad_x, int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream) {
     if (!e || !e->loaded) { set_error("parameters not loaded"); return VS_ERR_STATE; }
     if (!x || !emb || !mask || !grad_mask || !g || !workspace) { set_error("bad argument"); return VS_ERR_INVALID; }
     TrainWs w = train_carve(e, B, T, workspace);
@@ -167,6 +178,7 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
     const int F = e->d.num_freq, H = e->d.lstm_dim, E = e->d.emb_dim, N1 = e->d.fc1_dim, Fp = padded_freq(F), act = e->d.activation;
     const long long M = (long long)B * T;
     const int Mi = (int)M, KI = 8 * F + E;
+    const BnSync sync = bn_sync_of(e);
     e->launches = 0;
     prof_begin(e, st);
     // ---- head: mask = sigmoid(z2), z2 = y1 W2^T + b2, y1 = relu(rh W1^T + b1), rh = relu(h)
@@ -210,10 +222,13 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
     } else {
         TRK(e, KID_TR_GEMM, st, tr_gemm(w.gates, 8 * H, 1, e->wih_x, 8 * F, 1, w.dxcat, 8 * F, Mi, 8 * F, 8 * H, false, st));       // d X = da W_ih[:, :8F]
     }
+    // every LSTM / FC parameter gradient is enqueued: a data-parallel caller can start reducing them now (97 % of the bytes)
+    if (e->bwd_hook && e->bwd_hook(e->bwd_hook_user, VS_BWD_STAGE_LSTM_FC_DONE, stream) != 0) {
+        set_error("backward hook failed"); return VS_ERR_STATE;
+    }
     // ---- cnn8 (64 -> 8, BN, act) backward
-    TR(e, st, tr_bn_bwd_cols(act, w.dxcat, w.z7, w.stat + 7 * 256, e->bn_gamma[7], w.sums, w.dxcat, 8, F, M, e->num_sms, st));   // dxcat <- dz7 (in place)
-    k_sums_to_grads<<<1, 64, 0, st>>>(w.sums, g->bn_gamma[7], g->bn_beta[7], 8);
-    TR(e, st, cudaGetLastError());
+    TR(e, st, tr_bn_bwd_cols(act, w.dxcat, w.z7, w.stat + 7 * 256, e->bn_gamma[7], w.sums, w.dxcat, 8, F, M, e->num_sms, st,
+                             g->bn_gamma[7], g->bn_beta[7], sync));   // dxcat <- dz7 (in place)
     TR(e, st, tr_bn_stats_cols(w.dxcat, w.sums, 8, F, M, e->num_sms, st));
     k_sum0_to_float<<<1, 64, 0, st>>>(w.sums, g->conv_b[7], 8);
     TR(e, st, cudaGetLastError());
@@ -226,9 +241,8 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
         const bool tc_dgrad = e->train_tc && l >= 1;
         // tensor-core path: dz_l only as bf16 hi/lo planes (what wgrad and dgrad read); fp32 path: fp32 plane G2
         TRK(e, KID_TR_BN_BWD, st, tr_bn_bwd_plane(act, w.G1, w.z[l], w.stat + l * 256, e->bn_gamma[l], w.sums, tc_dgrad ? nullptr : w.G2, F, Fp, M,
-                                                  e->num_sms, st, tc_dgrad ? w.Dhi : nullptr, tc_dgrad ? w.Dlo : nullptr));
-        k_sums_to_grads<<<1, 64, 0, st>>>(w.sums, g->bn_gamma[l], g->bn_beta[l], 64);
-        TR(e, st, cudaGetLastError());
+                                                  e->num_sms, st, tc_dgrad ? w.Dhi : nullptr, tc_dgrad ? w.Dlo : nullptr, g->bn_gamma[l], g->bn_beta[l],
+                                                  sync));
         if (tc_dgrad) {
             // a conv bias in front of a BatchNorm has an exactly zero gradient (sum dz = -gamma rstd S2 sum(xhat) / N, sum(xhat) = 0)
             TR(e, st, cudaMemsetAsync(g->conv_b[l], 0, 64 * sizeof(float), st));
@@ -240,6 +254,7 @@ int vs_train_backward(vs_engine* e, const float* x, const float* emb, const floa
         if (l == 0) {
             TR(e, st, tr_front_wgrad(x, w.G2, w.dwp, F, Fp, M, e->num_sms, st));
             TR(e, st, tr_unpack_conv_grad(w.dwp, g->conv_w[0], 64, 1, 7, st));
+            if (grad_x) TRK(e, KID_TR_DGRAD, st, tr_front_dgrad(w.G2, e->conv_w32[0], grad_x, F, Fp, M, st));   // d loss / d spectrogram
             break;
         }
         if (e->train_tc) {   // a_{l-1} recomputed as bf16 hi/lo planes; weight gradient on tensor cores

@@ -555,6 +555,42 @@ __global__ void __launch_bounds__(256, 1) k_lstm_bwd_fp32(float* __restrict__ ga
     }
 }
 
+__global__ void k_sums_to_grads(const double* __restrict__ sums, float* dgamma, float* dbeta, int C) {
+    int c = threadIdx.x;
+    if (c < C) { if (dbeta) dbeta[c] = (float)sums[c]; if (dgamma) dgamma[c] = (float)sums[64 + c]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// d loss / d spectrogram: the transposed 1x7 filter of cnn1 applied to dz0, summed over the 64 channels.
+// One warp per output pixel pair is overkill: a thread owns one pixel and walks 7 taps x 16 float4 of channels;
+// neighbouring threads read neighbouring pixels (the 7-pixel windows overlap in L1).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_front_dgrad(const float* __restrict__ dz0, const float* __restrict__ w, float* __restrict__ dx,
+                                                     int F, int Fp, long long nrows) {
+    __shared__ __align__(16) float ws[7 * 64];
+    for (int i = threadIdx.x; i < 7 * 64; i += 256) ws[i] = w[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nrows * F) return;
+    const long long row = i / F;
+    const int f = (int)(i - row * F);
+    const float* zr = dz0 + (size_t)row * Fp * 64;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const int fs = f - j + 3;              // z0[fs] used x[fs + j - 3] = x[f] with tap j
+        if (fs < 0 || fs >= F) continue;
+        const float4* zp = reinterpret_cast<const float4*>(zr + (size_t)fs * 64);
+        const float4* wp = reinterpret_cast<const float4*>(ws + j * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 a = zp[q], b = wp[q];
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        }
+    }
+    dx[i] = acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------
@@ -595,32 +631,50 @@ cudaError_t tr_bn_act_cols(int act, const float* z, float* a, const float* stat,
                     (k_bn_act_cols<VS_ACT_RELU><<<grid, 256, 0, st>>>(z, a, stat, C, F, n)));
     return cudaGetLastError();
 }
+cudaError_t tr_bn_sync(const BnSync& sync, double* sums, cudaStream_t st) {
+    if (!sync.fn) return cudaSuccess;
+    if (sync.fn(sync.user, sums, 128, (void*)st) != 0) { set_error("SyncBN statistics all-reduce callback failed"); return cudaErrorUnknown; }
+    return cudaSuccess;
+}
+cudaError_t tr_front_dgrad(const float* dz0, const float* w, float* dx, int F, int Fp, long long nrows, cudaStream_t st) {
+    const long long n = nrows * F;
+    k_front_dgrad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz0, w, dx, F, Fp, nrows);
+    return cudaGetLastError();
+}
 cudaError_t tr_bn_bwd_plane(int act, const float* da, const float* z, const float* stat, const float* gamma, double* sums, float* dz,
-                            int F, int Fp, long long nrows, int num_sms, cudaStream_t st, elt16* dhi, elt16* dlo) {
+                            int F, int Fp, long long nrows, int num_sms, cudaStream_t st, elt16* dhi, elt16* dlo, float* dgamma, float* dbeta,
+                            const BnSync& sync) {
     cudaError_t e = cudaMemsetAsync(sums, 0, 128 * sizeof(double), st);
     if (e != cudaSuccess) return e;
     int grid = (int)(nrows < (long long)num_sms * 8 ? nrows : (long long)num_sms * 8);
     VS_ACT_DISPATCH(act, (k_bn_bwd_reduce_plane<VS_ACT_MISH><<<grid, 256, 0, st>>>(da, z, stat, sums, F, Fp, nrows)),
                     (k_bn_bwd_reduce_plane<VS_ACT_RELU><<<grid, 256, 0, st>>>(da, z, stat, sums, F, Fp, nrows)));
+    if (dgamma || dbeta) k_sums_to_grads<<<1, 64, 0, st>>>(sums, dgamma, dbeta, 64);
+    e = tr_bn_sync(sync, sums, st);
+    if (e != cudaSuccess) return e;
     const long long npix = nrows * Fp;
-    const double count = (double)nrows * F;
+    const double count = (double)nrows * F * sync.world;
     unsigned g2 = (unsigned)((npix * 16 + 255) / 256);
     VS_ACT_DISPATCH(act, (k_bn_bwd_apply_plane<VS_ACT_MISH><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix, dhi, dlo)),
                     (k_bn_bwd_apply_plane<VS_ACT_RELU><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, F, Fp, npix, dhi, dlo)));
     return cudaGetLastError();
 }
 cudaError_t tr_bn_bwd_cols(int act, const float* da, const float* z, const float* stat, const float* gamma, double* sums, float* dz,
-                           int C, int F, long long nrows, int num_sms, cudaStream_t st) {
+                           int C, int F, long long nrows, int num_sms, cudaStream_t st, float* dgamma, float* dbeta, const BnSync& sync) {
     cudaError_t e = cudaMemsetAsync(sums, 0, 128 * sizeof(double), st);
     if (e != cudaSuccess) return e;
     long long nf = nrows * F;
     int gx = (int)((nf + 255) / 256 < (long long)num_sms * 2 ? (nf + 255) / 256 : (long long)num_sms * 2);
     VS_ACT_DISPATCH(act, (k_bn_bwd_reduce_cols<VS_ACT_MISH><<<dim3(gx, C), 256, 0, st>>>(da, z, stat, sums, C, F, nrows)),
                     (k_bn_bwd_reduce_cols<VS_ACT_RELU><<<dim3(gx, C), 256, 0, st>>>(da, z, stat, sums, C, F, nrows)));
+    if (dgamma || dbeta) k_sums_to_grads<<<1, 64, 0, st>>>(sums, dgamma, dbeta, C);
+    e = tr_bn_sync(sync, sums, st);
+    if (e != cudaSuccess) return e;
     long long n = nrows * C * F;
     unsigned g2 = (unsigned)((n + 255) / 256);
-    VS_ACT_DISPATCH(act, (k_bn_bwd_apply_cols<VS_ACT_MISH><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, (double)nf, dz, C, F, n)),
-                    (k_bn_bwd_apply_cols<VS_ACT_RELU><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, (double)nf, dz, C, F, n)));
+    const double count = (double)nf * sync.world;
+    VS_ACT_DISPATCH(act, (k_bn_bwd_apply_cols<VS_ACT_MISH><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, C, F, n)),
+                    (k_bn_bwd_apply_cols<VS_ACT_RELU><<<g2, 256, 0, st>>>(da, z, stat, gamma, sums, count, dz, C, F, n)));
     return cudaGetLastError();
 }
 cudaError_t tr_conv_wgrad(const float* a, const float* dz, float* dwp, int T, int F, int Fp, int kh, int kw, int dil, long long nrows, cudaStream_t st) {

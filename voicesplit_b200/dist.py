@@ -57,17 +57,55 @@ def aggregate_throughput(local_units, local_ms, dist, device="cpu"):
     return total / (ms / 1e3), ms
 
 
-def allreduce_gradients(parameters, dist, world=None):
-    """Data-parallel step of BASELINE config 4: ONE all-reduce over a flat fp32 buffer holding every
-    parameter gradient (18.9 M floats = 75.5 MB at the shipped config), then divide by the world size
-    (the loss is a batch mean) and scatter back into the .grad tensors.  No-op for a single process."""
-    params = [p for p in parameters if p.grad is not None]
-    if dist is None or not params:
+def reduce_flat(flat, dist, async_op=False):
+    """Average `flat` over the ranks with ONE collective: NCCL averages inside the reduction (ReduceOp.AVG); backends without
+    AVG (gloo) sum and divide.  Returns the work handle when async_op (its .wait() orders the current stream behind it)."""
+    if dist.get_backend() == "nccl":
+        return dist.all_reduce(flat, op=dist.ReduceOp.AVG, async_op=async_op)
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
+    if async_op:
+        class _Div:
+            def wait(self_inner):
+                work.wait()
+                flat.div_(dist.get_world_size())
+        return _Div()
+    flat.div_(dist.get_world_size())
+    return None
+
+
+def allreduce_gradients(module_or_parameters, dist, world=None):
+    """Data-parallel step of BASELINE config 4: ONE all-reduce over a flat fp32 buffer holding every parameter gradient
+    (18.9 M floats = 75.5 MB at the shipped config), averaged over the ranks (the loss is a batch mean).
+
+    Fast path - a MaskEstimator whose .grad tensors are views of its flat gradient buffer (what its backward produces):
+    the buffer is reduced in place, no gather and no copy-back; if `enable_data_parallel(..., overlap=True)` started the
+    LSTM / FC tail during the backward, only the conv / BatchNorm head (2 MB) is reduced here and the tail is awaited.
+    Generic path (any iterable of parameters): gather into a temporary flat buffer, reduce, scatter back.
+    Returns the number of gradient elements reduced.  No-op for a single process."""
+    if dist is None:
         return 0
-    world = world or dist.get_world_size()
+    flat_of = getattr(module_or_parameters, "flat_gradient", None)
+    if flat_of is not None:
+        module = module_or_parameters
+        flat = flat_of()
+        if flat is not None:
+            pending, module._dp_pending = module._dp_pending, None
+            if pending is not None and pending[0] is flat:
+                _f, tail, work = pending
+                reduce_flat(flat[:tail], dist)
+                work.wait()
+            else:
+                if pending is not None:
+                    pending[2].wait()
+                reduce_flat(flat, dist)
+            return flat.numel()
+        params = [p for p in module.parameters() if p.grad is not None]
+    else:
+        params = [p for p in module_or_parameters if p.grad is not None]
+    if not params:
+        return 0
     flat = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world)
+    reduce_flat(flat, dist)
     off = 0
     for p in params:
         n = p.grad.numel()

@@ -18,6 +18,17 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+class _DeviceArray:
+    """Zero-copy view of raw device memory handed to a callback (CUDA array interface v2)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _wrap_device_array(ptr, count, typestr, device):
+    return torch.as_tensor(_DeviceArray(ptr, count, typestr), device=device)
+
+
 class MaskEngine:
     def __init__(self, num_freq, emb_dim, lstm_dim, fc1_dim, fc2_dim, activation="mish", device=None):
         self.lib = _cabi.load()
@@ -73,7 +84,9 @@ class MaskEngine:
             st = torch.cuda.current_stream().cuda_stream
             _cabi.check(self.lib.vs_engine_load_params(self.handle, ctypes.byref(p), ctypes.c_void_p(st)),
                         "vs_engine_load_params")
-            torch.cuda.current_stream().synchronize()  # staging copies in `keep` may now be released
+        # the packing kernels read the source tensors asynchronously: keep them (and any staging copies) referenced
+        # until the next load instead of synchronising the host on every optimizer step
+        self._keep = keep
 
     # ---- workspace ----------------------------------------------------------------------------
     def _workspace(self, B, T, prec):
@@ -368,6 +381,45 @@ class MaskEngine:
     def set_train_tensor_cores(self, on):
         _cabi.check(self.lib.vs_engine_set_train_tensor_cores(self.handle, 1 if on else 0), "vs_engine_set_train_tensor_cores")
 
+    # ---- data-parallel hooks (include/voicesplit_b200.h: vs_engine_set_sync_bn / vs_engine_set_backward_hook) ----
+    def set_sync_bn(self, allreduce_sum_doubles, world_size):
+        """allreduce_sum_doubles(tensor float64 [128] on this device) sums it in place across ranks (None: per-rank statistics)."""
+        if allreduce_sum_doubles is None:
+            self._sync_cb = ctypes.cast(None, _cabi.STAT_ALLREDUCE_FN)
+        else:
+            dev = self.device
+
+            def cb(_user, ptr, count, _stream):
+                try:
+                    allreduce_sum_doubles(_wrap_device_array(ptr, count, "<f8", dev))
+                    return 0
+                except Exception as ex:      # noqa: BLE001 - must not unwind through the C frame
+                    self._hook_error = ex
+                    return 1
+            self._sync_cb = _cabi.STAT_ALLREDUCE_FN(cb)
+        _cabi.check(self.lib.vs_engine_set_sync_bn(self.handle, self._sync_cb, None, int(world_size)), "vs_engine_set_sync_bn")
+
+    def set_backward_hook(self, fn):
+        """fn(stage) is called mid-backward (stage 1: LSTM / FC parameter gradients enqueued); None clears it."""
+        if fn is None:
+            self._bwd_cb = ctypes.cast(None, _cabi.BACKWARD_HOOK_FN)
+        else:
+            def cb(_user, stage, _stream):
+                try:
+                    fn(int(stage))
+                    return 0
+                except Exception as ex:      # noqa: BLE001
+                    self._hook_error = ex
+                    return 1
+            self._bwd_cb = _cabi.BACKWARD_HOOK_FN(cb)
+        _cabi.check(self.lib.vs_engine_set_backward_hook(self.handle, self._bwd_cb, None), "vs_engine_set_backward_hook")
+
+    def _check_hook(self, rc, what):
+        err, self._hook_error = getattr(self, "_hook_error", None), None
+        if err is not None:
+            raise RuntimeError(f"{what}: data-parallel hook raised") from err
+        _cabi.check(rc, what)
+
     def train_forward(self, x, emb, bn_buffers=None, momentum=0.1):
         """Forward in BatchNorm-training mode.  bn_buffers: {state_dict key: tensor} of the running_mean /
         running_var / num_batches_tracked buffers to update in place (or None).  Returns (mask, saved)."""
@@ -388,17 +440,37 @@ class MaskEngine:
                     state.num_batches_tracked[l] = bn_buffers[f"conv.{BN_IDX[l]}.num_batches_tracked"].data_ptr()
                 state.momentum = float(momentum)
             st = torch.cuda.current_stream().cuda_stream
-            _cabi.check(self.lib.vs_train_forward(self.handle, ctypes.byref(state) if state is not None else None, _ptr(x), _ptr(emb),
-                                                  _ptr(mask), B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_train_forward")
+            self._check_hook(self.lib.vs_train_forward(self.handle, ctypes.byref(state) if state is not None else None, _ptr(x), _ptr(emb),
+                                                       _ptr(mask), B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_train_forward")
         return mask, (ws, need, x, emb)
 
-    def train_backward(self, saved, mask, grad_mask, shapes):
-        """shapes: {state_dict key: shape} of the parameters.  Returns ({key: grad tensor}, grad_emb)."""
+    @classmethod
+    def grad_layout(cls, shapes):
+        """{key: (offset, numel)} of every parameter gradient inside ONE flat fp32 buffer, in PARAM_ORDER (conv / BatchNorm
+        first, then LSTM, then FC: the last two are a contiguous tail), and the total element count."""
+        off, lay = 0, {}
+        for k in cls.PARAM_ORDER:
+            n = 1
+            for d in shapes[k]:
+                n *= int(d)
+            lay[k] = (off, n)
+            off += n
+        return lay, off
+
+    def train_backward(self, saved, mask, grad_mask, shapes, flat=None, want_grad_x=False):
+        """shapes: {state_dict key: shape} of the parameters.  Gradients are written into `flat` (one fp32 buffer in
+        grad_layout order, allocated here if None) and returned as views of it: ({key: grad}, grad_emb, grad_x or None)."""
         ws, need, x, emb = saved
         B, T, _ = x.shape
         grad_mask = grad_mask.detach().to(torch.float32).contiguous()
-        grads = {k: torch.empty(shapes[k], dtype=torch.float32, device=x.device) for k in self.PARAM_ORDER}
+        lay, total = self.grad_layout(shapes)
+        if flat is None:
+            flat = torch.empty(total, dtype=torch.float32, device=x.device)
+        if flat.numel() != total or flat.dtype != torch.float32 or flat.device != x.device:
+            raise ValueError("flat gradient buffer does not match the parameter shapes")
+        grads = {k: flat[o:o + n].view(shapes[k]) for k, (o, n) in lay.items()}
         gemb = torch.empty_like(emb)
+        gx = torch.empty_like(x) if want_grad_x else None
         g = _cabi.VsGrads()
         for l in range(8):
             g.conv_w[l] = grads[f"conv.{CONV_IDX[l]}.weight"].data_ptr(); g.conv_b[l] = grads[f"conv.{CONV_IDX[l]}.bias"].data_ptr()
@@ -410,9 +482,9 @@ class MaskEngine:
         g.fc2_w, g.fc2_b = grads["fc2.weight"].data_ptr(), grads["fc2.bias"].data_ptr()
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream
-            _cabi.check(self.lib.vs_train_backward(self.handle, _ptr(x), _ptr(emb), _ptr(mask), _ptr(grad_mask), ctypes.byref(g), _ptr(gemb),
-                                                   B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_train_backward")
-        return grads, gemb
+            self._check_hook(self.lib.vs_train_backward(self.handle, _ptr(x), _ptr(emb), _ptr(mask), _ptr(grad_mask), ctypes.byref(g), _ptr(gemb),
+                                                        _ptr(gx), B, T, _ptr(ws), need, ctypes.c_void_p(st)), "vs_train_backward")
+        return grads, gemb, gx
 
     # ---- test hooks ---------------------------------------------------------------------------
     def debug_conv_layer(self, layer, inp, precision="fp32"):
