@@ -90,3 +90,49 @@ def test_si_snr_matches_reference_formula():
         _, _, gu = ref_import.load()
         ref = gu.SiSNR_With_Pit()(est.clone(), src.clone(), lengths)
         assert torch.allclose(mine, ref, atol=1e-5)
+
+
+class _FakeFlatModule:
+    """Stands in for a MaskEstimator after its backward: .grad tensors are views of ONE flat buffer (no GPU needed)."""
+
+    def __init__(self, rank):
+        self.flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        self.params = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4))]
+        self.params[0].grad = self.flat[0:6].view(2, 3)
+        self.params[1].grad = self.flat[6:10]
+        self._dp_pending = None
+
+    def parameters(self):
+        return iter(self.params)
+
+    def flat_gradient(self):
+        return self.flat
+
+
+def _flat_worker(rank, world, port, overlap, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    d = vdist.init("gloo")
+    m = _FakeFlatModule(rank)
+    if overlap:     # what MaskEstimator._dp_stage does mid-backward: the tail of the buffer is already being reduced
+        m._dp_pending = (m.flat, 6, vdist.reduce_flat(m.flat[6:], d, async_op=True))
+    n = vdist.allreduce_gradients(m, d)
+    if rank == 0:
+        out.put((n, m.flat.tolist(), m.params[0].grad.data_ptr() == m.flat.data_ptr(), m._dp_pending is None))
+    d.barrier()
+    d.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_flat_buffer_fast_path_reduces_in_place(overlap):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n, flat, aliased, pending = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n == 10 and aliased and pending
+    assert torch.allclose(torch.tensor(flat), torch.arange(10, dtype=torch.float32) * 1.5)     # mean of (1x, 2x), every element exactly once

@@ -125,8 +125,9 @@ def test_module_forward_matches_golden_and_repacks_after_update():
     assert (mask2 > mask).float().mean() > 0.99
     out = m.train()(x, emb)                    # training mode: batch statistics, autograd graph attached
     assert out.requires_grad and out.shape == x.shape
-    with pytest.raises(NotImplementedError):   # the gradient w.r.t. the spectrogram is not provided
-        m(x.clone().requires_grad_(True), emb)
+    xg = x.clone().requires_grad_(True)        # differentiable w.r.t. the spectrogram as well (SURVEY 8b "and inputs")
+    m(xg, emb).sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all() and float(xg.grad.abs().max()) > 0
 
 
 @pytest.mark.parametrize("precision", CONV_MODES)

@@ -19,9 +19,29 @@ def _cpu_reference(sd_np, x, emb, gw, activation):
             t.requires_grad_(True)
         sd[k] = t
     et = torch.from_numpy(emb).requires_grad_(True)
-    mask = torch_port.forward_train(sd, torch.from_numpy(x), et, activation)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    mask = torch_port.forward_train(sd, xt, et, activation)
     (mask * torch.from_numpy(gw)).sum().backward()
-    return mask.detach(), sd, et.grad
+    return mask.detach(), sd, et.grad, xt.grad
+
+
+def _compare_gradients(m, ref_sd, rel=2e-3):
+    """Every parameter gradient against autograd, relative to the gradient's own scale; a conv bias in front of a BatchNorm
+    has an analytically ZERO gradient (the batch mean removes it), so both sides hold rounding noise there: those are
+    judged on the scale of their layer's weight gradient."""
+    gmax = max(float(ref_sd[k].grad.abs().max()) for k, _ in m.named_parameters())
+    worst = {}
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        r = ref_sd[k].grad
+        worst[k] = (float((p.grad.cpu() - r).abs().max()), float(r.abs().max()))
+    conv_bias = {f"conv.{i}.bias": f"conv.{i}.weight" for i in (1, 5, 9, 13, 17, 21, 25, 28)}
+
+    def scale(k):
+        return max(worst[k][1], worst[conv_bias[k]][1]) if k in conv_bias else worst[k][1]
+    bad = {k: v for k, v in worst.items() if v[0] > rel * scale(k) + 1e-6 * gmax}
+    print({k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in worst.items()})
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("tensor_cores", [True, False])
@@ -34,7 +54,7 @@ def test_train_forward_backward_match_autograd(model_name, dims, B, T, tensor_co
     sd_np = synth.make_state_dict(dims, 5, "stress")
     x, emb = synth.make_inputs(B, T, dims, 6)
     gw = np.random.default_rng(0).standard_normal((B, T, dims["num_freq"])).astype(np.float32)
-    ref_mask, ref_sd, ref_gemb = _cpu_reference(sd_np, x, emb, gw, model_name)
+    ref_mask, ref_sd, ref_gemb, ref_gx = _cpu_reference(sd_np, x, emb, gw, model_name)
 
     cls = VoiceSplit if model_name == "voicesplit" else VoiceFilter
     m = cls(config.AttrDict(synth.make_config_dict(dims, model_name)))
@@ -42,7 +62,8 @@ def test_train_forward_backward_match_autograd(model_name, dims, B, T, tensor_co
     m = m.cuda().train()
     m.train_tensor_cores = tensor_cores
     et = torch.from_numpy(emb).cuda().requires_grad_(True)
-    mask = m(torch.from_numpy(x).cuda(), et)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)          # the module is differentiable w.r.t. its inputs too
+    mask = m(xt, et)
     assert mask.requires_grad
     (mask * torch.from_numpy(gw).cuda()).sum().backward()
     torch.cuda.synchronize()
@@ -54,23 +75,13 @@ def test_train_forward_backward_match_autograd(model_name, dims, B, T, tensor_co
             assert torch.allclose(msd[k].cpu(), ref_sd[k], atol=2e-5, rtol=1e-4), k
         if "num_batches" in k:
             assert int(msd[k]) == 1
-    # relative to each gradient's own scale; a conv bias in front of a BatchNorm has an analytically ZERO
-    # gradient (the batch mean removes it), so both sides hold rounding noise there: absolute floor
-    gmax = max(float(ref_sd[k].grad.abs().max()) for k, _ in m.named_parameters())
-    worst = {}
-    for k, p in m.named_parameters():
-        assert p.grad is not None, k
-        r = ref_sd[k].grad
-        err = float((p.grad.cpu() - r).abs().max())
-        worst[k] = (err, float(r.abs().max()))
-    conv_bias = {f"conv.{i}.bias": f"conv.{i}.weight" for i in (1, 5, 9, 13, 17, 21, 25, 28)}
-
-    def scale(k):   # analytically-zero conv-bias gradients are judged on the scale of their layer's weight gradient
-        return max(worst[k][1], worst[conv_bias[k]][1]) if k in conv_bias else worst[k][1]
-    bad = {k: v for k, v in worst.items() if v[0] > 2e-3 * scale(k) + 1e-6 * gmax}
-    print({k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in worst.items()})
-    assert not bad, bad
+    _compare_gradients(m, ref_sd)
     assert (et.grad.cpu() - ref_gemb).abs().max() < 2e-3 * max(1e-6, float(ref_gemb.abs().max()))
+    assert (xt.grad.cpu() - ref_gx).abs().max() < 2e-3 * max(1e-6, float(ref_gx.abs().max()))
+    # the gradients live in ONE flat buffer (what the data-parallel all-reduce sends), .grad tensors are views of it
+    flat = m.flat_gradient()
+    assert flat is not None and flat.numel() == sum(p.numel() for p in m.parameters())
+    assert m.fc2.bias.grad.data_ptr() == flat.data_ptr() + 4 * (flat.numel() - m.fc2.bias.numel())
 
 
 def test_adam_step_changes_the_mask_and_repacks():
@@ -94,3 +105,94 @@ def test_adam_step_changes_the_mask_and_repacks():
     m.eval()
     with torch.no_grad():
         assert torch.isfinite(m(xt, et)).all()
+
+
+@pytest.mark.parametrize("dims,B,T", [(synth.make_dims(601), 1, 301), (synth.make_dims(257), 2, 601)])
+def test_full_size_gradients_match_autograd(dims, B, T):
+    """BASELINE shapes (native 301 x 601 and literal 601 x 257), stress weights: the gradient of all 44 parameters, of the
+    d-vector and of the spectrogram against PyTorch autograd on the CPU - the tensor-core wgrad's flush-every-16-chunks
+    accumulation, the bf16x3 gradient planes and the double-atomic BatchNorm sums at 180 k pixels per utterance."""
+    from models.voicesplit.model import VoiceSplit
+    sd_np = synth.make_state_dict(dims, 15, "stress")
+    x, emb = synth.make_inputs(B, T, dims, 16)
+    gw = np.random.default_rng(1).standard_normal((B, T, dims["num_freq"])).astype(np.float32)
+    ref_mask, ref_sd, ref_gemb, ref_gx = _cpu_reference(sd_np, x, emb, gw, "voicesplit")
+    m = VoiceSplit(config.AttrDict(synth.make_config_dict(dims)))
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    m = m.cuda().train()
+    et = torch.from_numpy(emb).cuda().requires_grad_(True)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    mask = m(xt, et)
+    (mask * torch.from_numpy(gw).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    d = (mask.detach().cpu() - ref_mask).abs()
+    print(f"train-mode mask {T}x{dims['num_freq']}: max {float(d.max()):.2e} mean {float(d.mean()):.2e}")
+    assert d.max() < 1e-3 and d.mean() < 1e-4
+    msd = m.state_dict()
+    for k in msd:
+        if "running" in k:
+            assert torch.allclose(msd[k].cpu(), ref_sd[k], atol=5e-5, rtol=2e-4), k
+    _compare_gradients(m, ref_sd, rel=5e-3)
+    assert (et.grad.cpu() - ref_gemb).abs().max() < 5e-3 * float(ref_gemb.abs().max())
+    assert (xt.grad.cpu() - ref_gx).abs().max() < 5e-3 * float(ref_gx.abs().max())
+
+
+def test_eval_after_train_forward_uses_the_updated_running_statistics():
+    """train-mode forwards update running_mean / running_var through raw pointers; with no optimizer
+    step in between (BN recalibration under no_grad) a following eval() must still fold the NEW statistics."""
+    from models.voicesplit.model import VoiceSplit
+    dims = synth.make_dims(33, 16, 24, 40)
+    sd_np = synth.make_state_dict(dims, 3, "stress")
+    x, emb = synth.make_inputs(3, 17, dims, 4)
+    m = VoiceSplit(config.AttrDict(synth.make_config_dict(dims)))
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    m = m.cuda().eval()
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
+    with torch.no_grad():
+        before = m(xt, et).clone()
+        m.train()
+        for _ in range(3):
+            m(xt, et)                       # three recalibration passes, no backward, no optimizer
+        m.eval()
+        after = m(xt, et)
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()}
+    for _ in range(3):
+        torch_port.forward_train(sd, torch.from_numpy(x), torch.from_numpy(emb))
+    ref = torch_port.forward(sd, torch.from_numpy(x), torch.from_numpy(emb))
+    assert (before - after).abs().max() > 1e-3            # the statistics did change the mask
+    assert (after.cpu() - ref).abs().max() < 1e-3
+
+
+def test_second_backward_through_the_same_forward_raises():
+    """the backward consumes the saved workspace in place; reuse must raise instead of returning garbage."""
+    from models.voicesplit.model import VoiceSplit
+    dims = synth.make_dims(17, 8, 16, 24)
+    m = VoiceSplit(config.AttrDict(synth.make_config_dict(dims))).cuda().train()
+    x, emb = synth.make_inputs(2, 9, dims, 1)
+    mask = m(torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda())
+    mask.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="consumed"):
+        mask.sum().backward()
+
+
+def test_gradient_accumulation_over_two_backwards_is_a_sum():
+    """Two micro-batches without zero_grad in between: .grad must hold the SUM (autograd adds the second gradient to the
+    first, so the second backward may not write into the buffer the first gradient lives in)."""
+    from models.voicesplit.model import VoiceSplit
+    dims = synth.make_dims(17, 8, 16, 24)
+    m = VoiceSplit(config.AttrDict(synth.make_config_dict(dims))).cuda().train()
+    for bn in (mod for mod in m.conv if isinstance(mod, torch.nn.BatchNorm2d)):
+        bn.momentum = 0.0                # keep the running statistics fixed so both passes are the same function
+    xs = [synth.make_inputs(2, 9, dims, s) for s in (1, 2)]
+    singles = []
+    for x, emb in xs:
+        m.zero_grad(set_to_none=True)
+        m(torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()).square().sum().backward()
+        singles.append({k: p.grad.clone() for k, p in m.named_parameters()})
+    m.zero_grad(set_to_none=True)
+    for x, emb in xs:
+        m(torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()).square().sum().backward()
+    for k, p in m.named_parameters():
+        want = singles[0][k] + singles[1][k]
+        assert torch.allclose(p.grad, want, rtol=1e-4, atol=1e-6 * float(want.abs().max() + 1e-30)), k
+    assert m.flat_gradient() is not None       # still the views of the first buffer

@@ -22,10 +22,18 @@
 // quadrant, each taking every fourth 32-column chunk, so every SM sub-partition has four warps to
 // hide the MUFU/shuffle latency of the Mish epilogue).  Two TMEM accumulators of N columns
 // double-buffer MMA against the epilogue; the CTA is persistent over tiles.
+//
+// Weight multicast.  Every CTA walks the same sequence of weight tiles (15 steps x 32 KB per 5x5 tile = 480 KB, more than the
+// 338 KB of pixel strips), and once the MMA work per tile drops to 8 slots per step (FP16_F8C) the L2 -> SM fill, not the tensor
+// pipe, bounds the kernel (chip-wide L2 throughput ~6.3 KB/clk = 43 B/clk/SM).  CTAs are therefore launched as thread-block
+// clusters that share ONE fetch of each weight tile: CTA r of the cluster loads rows [r, r+1) * 128/csz of the tile and TMA
+// multicasts them into every member's ring slot; a slot is refilled only after the MMA threads of ALL members have committed
+// it (tcgen05.commit multicast onto every member's w_empty barrier, count = cluster size).
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
+#include <stdlib.h>
 
 namespace vs {
 using namespace ptx;
@@ -44,6 +52,7 @@ struct ConvTcArgs {
     int passes;           // 1 (single 16-bit pass) or 3 (two operand planes: hi/lo split, or hi + fp8 correction plane)
     int f8c;              // VS_PREC_FP16_F8C: second plane = e4m3 correction operands, 4 f16 + 4 f8f6f4 MMAs per tap pair
     int strip_rows, box_rows, n_boxes, s_stages;
+    int csz, n_iter;      // cluster size sharing the weight fetches; tile iterations every CTA runs (the same for all: lock step)
     int act;
     const float* scale;
     const float* shift;
@@ -79,8 +88,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = a.csz > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << a.csz) - 1u);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], (uint32_t)a.csz); }
         for (int i = 0; i < a.s_stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_barrier_init();
@@ -97,6 +108,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
     }
     tc_fence_before();
     __syncthreads();
+    if (a.csz > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts onto them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int useful = a.N - 1;
@@ -108,12 +120,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
         if (lane == 0) {
             // ===================== TMA producer =====================
             int ws = 0, wph = 0, ss = 0, sph = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int b = tile / a.tiles_per_utt;
+            const int slice_rows = 128 / a.csz;
+            for (int itn = 0; itn < a.n_iter; ++itn) {
+                const int tile = blockIdx.x + itn * gridDim.x;
+                const bool valid = tile < a.total_tiles;    // a padding iteration still takes part in the shared weight stream
+                const int b = valid ? tile / a.tiles_per_utt : 0;
                 const int q0 = (tile - b * a.tiles_per_utt) * useful;
                 for (int dt = 0; dt < a.n_dt; ++dt) {
                     const int qs = q0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
-                    for (int sp = 0; sp < n_strip_loads; ++sp) {  // strip planes of this tap row: hi (, lo)
+                    for (int sp = 0; valid && sp < n_strip_loads; ++sp) {  // strip planes of this tap row: hi (, lo)
                         mbar_wait(&s_empty[ss], sph ^ 1);
                         mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
                         uint8_t* dst = s_ring + (size_t)ss * strip_bytes;
@@ -125,15 +140,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                     // weight tiles of this tap row: W_hi[j] (used against both strips), then W_lo[j]
                     for (int j = 0; j < a.n_j; ++j) {
                         for (int wp = 0; wp < n_strip_loads; ++wp) {
-                            mbar_wait(&w_empty[ws], wph ^ 1);
+                            mbar_wait(&w_empty[ws], wph ^ 1);        // released by the MMA threads of all cluster members
                             mbar_arrive_expect_tx(&w_full[ws], kWTileBytes);
-                            tma_load_2d(w_ring + (size_t)ws * kWTileBytes, wp == 0 ? &tm_w_hi : &tm_w_lo, &w_full[ws], 0,
-                                        (dt * a.n_j + j) * 128);
+                            const void* tm = wp == 0 ? (const void*)&tm_w_hi : (const void*)&tm_w_lo;
+                            if (a.csz > 1)
+                                tma_load_2d_mc(w_ring + (size_t)ws * kWTileBytes + (size_t)crank * slice_rows * 128, tm, &w_full[ws], 0,
+                                               (dt * a.n_j + j) * 128 + (int)crank * slice_rows, cmask);
+                            else
+                                tma_load_2d(w_ring + (size_t)ws * kWTileBytes, tm, &w_full[ws], 0, (dt * a.n_j + j) * 128);
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                     }
                 }
             }
+            // drain: every arrival peers still owe this CTA's w_empty barriers has landed before the CTA may exit
+            if (a.csz > 1)
+                for (int i = 0; i < kWStages; ++i) {
+                    mbar_wait(&w_empty[ws], wph ^ 1);
+                    if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -141,8 +166,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
             const uint32_t idesc = make_idesc_bf16(128, a.N, ELT);
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
             int ws = 0, wph = 0, ss = 0, sph = 0, it = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            for (int itn = 0; itn < a.n_iter; ++itn) {
+                if (blockIdx.x + itn * gridDim.x >= a.total_tiles) {
+                    // padding iteration: no pixels, but the cluster's shared weight stages must still be consumed and released
+                    for (int n = a.n_dt * a.n_j * n_strip_loads; n > 0; --n) {
+                        mbar_wait(&w_full[ws], wph);
+                        if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
+                        if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                    }
+                    continue;
+                }
                 const int buf = it & 1, aph = (it >> 1) & 1;
+                ++it;
                 mbar_wait(&acc_empty[buf], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)(buf * a.N);
@@ -189,7 +224,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                                     }
                                 }
                             }
-                            umma_commit(&w_empty[ws]);
+                            if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                     }
@@ -282,6 +317,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
     }
     tc_fence_before();
     __syncthreads();
+    if (a.csz > 1) cluster_sync_all();     // nobody leaves while a peer may still multicast into its shared memory
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -529,6 +565,7 @@ struct TcState {
     float* unscale[8] = {};   // 64 copies of 1 / (power-of-two weight scale): epilogue scale of the raw-output convs
     unsigned int* wmax = nullptr;
     int max_smem = 0;
+    int cluster = 2;          // CTAs per cluster sharing the conv weight fetches (VOICESPLIT_CONV_CLUSTER = 1, 2, 4 or 8)
 };
 
 static int tile_n_for(const vs_engine*) { return 256; }
@@ -537,6 +574,10 @@ int tc_create(vs_engine* e) {
     TcState* s = new TcState();
     e->tc = s;
     cudaDeviceGetAttribute(&s->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+    if (const char* c = getenv("VOICESPLIT_CONV_CLUSTER")) {
+        const int v = atoi(c);
+        if (v == 1 || v == 2 || v == 4 || v == 8) s->cluster = v;
+    }
     return VS_OK;
 }
 void tc_destroy(vs_engine* e) {
@@ -668,12 +709,39 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
         ok = ok && make_tmap_bf16(&tm_w_lo, (void*)call.w_lo, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
         if (!ok) { set_error("cuTensorMapEncodeTiled failed"); return VS_ERR_CUDA; }
     }
-    int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
+    // cluster size sharing the weight fetches (see the header comment); grid = whole clusters, at most what is co-resident
+    a.csz = s->cluster;
+    if (a.csz > 1) {   // weight tiles arrive as 128 / csz-row slices, one per cluster member
+        uint64_t wd[2] = {64, (uint64_t)a.n_dt * a.n_j * 128};
+        uint64_t ws[1] = {128};
+        uint32_t wb[2] = {64, (uint32_t)(128 / a.csz)};
+        bool ok = make_tmap_bf16(&tm_w_hi, (void*)call.w_hi, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w_lo, (void*)call.w_lo, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!ok) { set_error("cuTensorMapEncodeTiled failed (weight slices)"); return VS_ERR_CUDA; }
+    }
     cudaError_t ce;
+    int grid = 0;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = a.csz > 1 ? 1 : 0;
 #define VS_CONV_TC(A, E, O, F8)                                                                               \
     do {                                                                                                      \
         ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-        if (ce == cudaSuccess) k_conv_tc<A, E, O, F8><<<grid, kConvThreads, smem, st>>>(a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+        int max_ctas = e->num_sms;                                                                            \
+        if (ce == cudaSuccess && a.csz > 1) {                                                                 \
+            int ncl = 0;                                                                                      \
+            cfg.gridDim = dim3((unsigned)(e->num_sms / a.csz * a.csz));                                       \
+            ce = cudaOccupancyMaxActiveClusters(&ncl, k_conv_tc<A, E, O, F8>, &cfg);                           \
+            if (ce == cudaSuccess && ncl < 1) { set_error("conv clusters do not fit the device"); return VS_ERR_UNSUPPORTED; } \
+            max_ctas = ncl * a.csz < e->num_sms ? ncl * a.csz : e->num_sms / a.csz * a.csz;                    \
+        }                                                                                                     \
+        grid = a.total_tiles < max_ctas ? (a.total_tiles + a.csz - 1) / a.csz * a.csz : max_ctas;             \
+        a.n_iter = (a.total_tiles + grid - 1) / grid;                                                         \
+        cfg.gridDim = dim3((unsigned)grid);                                                                   \
+        if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_conv_tc<A, E, O, F8>, a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
     if (call.out32) {
         if (call.act != 2) { set_error("fp32-output conv is pass-through only"); return VS_ERR_INVALID; }
