@@ -1,15 +1,17 @@
 """bench.py - utterances/s of the speaker-conditioned mask-estimation forward pass on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16x3|bf16x3|fp16|bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16_f8c|fp16x3|bf16x3|fp16|bf16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path (CNN -> BiLSTM -> FC -> sigmoid mask -> mask * spectrogram)
-over one batch of synthetic utterances.  Workload (BASELINE.json): `--batch` utterances per GPU of
+over one batch of synthetic utterances.  Workload (BASELINE.json configs[2]): `--batch` utterances per GPU of
 601 frames x 257 bins + a random 256-d d-vector, random-init ("stress" flavour) weights of the
 reference architecture.  Utterances are independent, so the batch is sharded across ranks with no
 data-path collective (weak scaling; the only collective is the max-over-ranks of the timings).
 
-One JSON line is printed by rank 0; keys are documented in DESIGN.md ("Measurement").
+One JSON line is printed by rank 0; keys are documented in DESIGN.md ("Measurement").  Besides the headline it carries
+  train_config4   (every N)  BASELINE configs[3]: forward + Si-SNR loss chain + backward + ONE NCCL gradient all-reduce + Adam
+  config2_conv_stack_b64, stock_torch_gpu_baseline, other_precisions, cpu_baseline, extras   (N = 1 only)
 """
 from __future__ import annotations
 
@@ -30,13 +32,29 @@ if ROOT not in sys.path:
 
 from voicesplit_b200 import synth  # noqa: E402
 
+METRIC = "utterances/s (601-frame, 257-bin spectrogram) masked"
+# MMA issue slots per tap-pair step relative to one fp16 pass (4 kind::f16 MMAs of K = 16 over the 64 input channels);
+# an e4m3 MMA covers K = 32 in the same time, so the fp8 correction pass of fp16_f8c is one more slot-equivalent
+PASS_EQUIV = {"bf16x3": 3, "fp16x3": 3, "fp16_f8c": 2, "bf16": 1, "fp16": 1}
+DTYPE = {"bf16x3": "bf16x3 (split-bf16 operands hi+lo, 3 MMAs, fp32 accumulate)",
+         "fp16x3": "fp16x3 (split-fp16 operands hi+lo, 3 MMAs, fp32 accumulate)",
+         "fp16_f8c": "fp16 + e4m3 correction (conv stack: 4 kind::f16 + 4 kind::f8f6f4 MMAs per tap pair into one fp32 accumulator; LSTM/FC fp16x3)",
+         "bf16": "bf16", "fp16": "f16", "fp32": "f32"}
+
+
 # algorithmic forward FLOPs (2 x MAC) per utterance, SURVEY.md section 8(d)
 def flops_per_utt(T, F, E=256, H=400, N1=600):
     P = T * F
     conv = 2 * P * (64 * 7 + 64 * 64 * 7 + 5 * 64 * 64 * 25 + 64 * 8)
-    lstm = 2 * T * (8 * F * 8 * H) + 2 * (E * 8 * H) + 2 * T * 2 * (H * 4 * H)
+    lstm_proj = 2 * T * (8 * F * 8 * H) + 2 * (E * 8 * H)
+    lstm_rec = 2 * T * 2 * (H * 4 * H)
     fc = 2 * T * (2 * H * N1 + N1 * F)
-    return dict(conv=conv, conv5x5_layer=2 * P * 64 * 64 * 25, lstm=lstm, fc=fc, total=conv + lstm + fc)
+    return dict(conv=conv, conv5x5_layer=2 * P * 64 * 64 * 25, lstm=lstm_proj + lstm_rec, lstm_input_proj=lstm_proj,
+                lstm_recurrence=lstm_rec, fc=fc, total=conv + lstm_proj + lstm_rec + fc)
+
+
+def padded_f(F):
+    return (F + 2 + 7) // 8 * 8
 
 
 def load_peaks():
@@ -101,60 +119,75 @@ def _usable_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_throughput(dims, T, seconds_budget=20.0, steps=1, warmup=1):
-    """The reference's CPU implementation of the path (the same torch.nn ATen ops the reference module
-    issues, restated in oracle/torch_port.py; /root/reference itself does not exist on the GPU box)
-    on a bounded sample of the workload: B_s utterances of the same T x F.  The thread count is the
-    best of a short sweep (all cores is not always fastest for oneDNN on a many-core host)."""
+def cpu_model_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_throughput(dims, T, runs=5, warmup=1, batches=(1, 8), seconds_cap=150.0):
+    """The reference's CPU implementation of the path - the same torch.nn ATen ops the reference module issues, restated in
+    oracle/torch_port.py (/root/reference itself does not exist on the GPU box) - following BASELINE.md section 4:
+    fp32, eval mode, B = 1 and B = 8 utterances of the FULL T x F, median of >= 5 runs after a warm-up, thread count the
+    best of a sweep done at the full T (all cores is not always fastest for oneDNN on a many-core host).  Returns the
+    cpu_baseline dict (value = the better of the two batch sizes) and the seconds of one median step."""
     from oracle import torch_port
     cores = _usable_cores()
     sd = {k: torch.from_numpy(v) for k, v in synth.make_state_dict(dims, 0, "stress").items() if v.dtype == np.float32}
-    xs, es = synth.make_inputs(1, max(16, T // 8), dims, 98)           # short probe for the thread sweep
-    xs, es = torch.from_numpy(xs), torch.from_numpy(es)
-    best, best_t = None, cores
+    x1, e1 = synth.make_inputs(1, T, dims, 99)
+    x1, e1 = torch.from_numpy(x1), torch.from_numpy(e1)
+    t_start = time.perf_counter()
+    sweep = {}
     for nt in sorted({cores, max(1, cores // 2), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
         torch.set_num_threads(nt)
-        torch_port.forward(sd, xs, es)
+        torch_port.forward(sd, x1, e1)
         t0 = time.perf_counter()
-        torch_port.forward(sd, xs, es)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, best_t = dt, nt
+        torch_port.forward(sd, x1, e1)
+        sweep[nt] = time.perf_counter() - t0
+    best_t = min(sweep, key=sweep.get)
     torch.set_num_threads(best_t)
-    x, emb = synth.make_inputs(1, T, dims, 99)
-    xt, et = torch.from_numpy(x), torch.from_numpy(emb)
-    t0 = time.perf_counter()
-    torch_port.forward(sd, xt, et)                      # warm-up (also sizes the sample)
-    one = time.perf_counter() - t0
-    bs = int(max(1, min(8, (seconds_budget / max(steps + warmup - 1, 1)) // max(one, 1e-3))))
-    x, emb = synth.make_inputs(bs, T, dims, 99)
-    xt, et = torch.from_numpy(x), torch.from_numpy(emb)
-    for _ in range(max(warmup - 1, 0)):
-        torch_port.forward(sd, xt, et)
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        torch_port.forward(sd, xt, et)
-        times.append(time.perf_counter() - t0)
-    dt = float(np.sum(times))
-    return dict(value=bs * steps / dt, unit="utterances/s", cores=best_t, kind="port",
-                sample=f"{bs} utterance(s) x {steps} step(s) of {T}x{dims['num_freq']} through oracle/torch_port.py "
-                       f"(the reference's own torch.nn CPU ops, fp32, {best_t} of {cores} host threads: best of a sweep), "
-                       f"{dt:.1f} s"), dt / steps
+    per_batch = {}
+    for bs in batches:
+        x, emb = synth.make_inputs(bs, T, dims, 99)
+        xt, et = torch.from_numpy(x), torch.from_numpy(emb)
+        for _ in range(max(warmup, 1)):
+            torch_port.forward(sd, xt, et)
+        times = []
+        for _ in range(max(runs, 5)):
+            t0 = time.perf_counter()
+            torch_port.forward(sd, xt, et)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > seconds_cap and len(times) >= 3:
+                break
+        per_batch[bs] = dict(median_s=float(np.median(times)), runs=len(times), utt_per_s=bs / float(np.median(times)))
+    best_b = max(per_batch, key=lambda b: per_batch[b]["utt_per_s"])
+    return dict(value=per_batch[best_b]["utt_per_s"], unit="utterances/s", cores=best_t, kind="port",
+                host=f"{cpu_model_name()}, {cores} usable cores",
+                per_batch={str(b): v for b, v in per_batch.items()}, thread_sweep_s={str(k): round(v, 4) for k, v in sweep.items()},
+                sample=f"B = {', '.join(str(b) for b in batches)} utterance(s) of {T}x{dims['num_freq']} through oracle/torch_port.py (the reference's own "
+                       f"torch.nn CPU ops, fp32, eval), median of {per_batch[best_b]['runs']} runs after warm-up, {best_t} of {cores} host "
+                       f"threads (best of a sweep at the full T); value = B = {best_b}"), per_batch[best_b]["median_s"]
 
 
+# =====================================================================================================================
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VOICESPLIT_PRECISION", "fp16x3"))
+    ap.add_argument("--precision", default=os.environ.get("VOICESPLIT_BENCH_PRECISION", "fp16_f8c"))
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=601)
     ap.add_argument("--freq", type=int, default=257)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary config-4 / config-5 measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip every secondary block (training, config 2, baselines)")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-4 training block")
+    ap.add_argument("--train-batch", type=int, default=256, help="config 4: utterances per GPU to try first (halved until it fits)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -173,8 +206,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb, step_s = cpu_reference_throughput(dims, T, seconds_budget=60.0, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
-        line = {"impl": "reference", "metric": "utterances/s (601-frame, 257-bin spectrogram) masked", "value": cb["value"],
+        cb, step_s = cpu_reference_throughput(dims, T, runs=max(args.steps, 5), warmup=max(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"],
                 "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
@@ -192,8 +225,8 @@ def main():
     eng = MaskEngine(activation="mish", device=dev, **dims)
     sd = synth.make_state_dict(dims, 0, "stress")
     eng.load_state_dict_tensors({k: torch.from_numpy(v).to(dev) for k, v in sd.items() if v.dtype == np.float32})
-    xh, eh = synth.make_inputs(B, T, dims, 1234 + rank)
-    xh, eh = torch.from_numpy(xh).pin_memory(), torch.from_numpy(eh).pin_memory()
+    xnp, enp = synth.make_inputs(B, T, dims, 1234 + rank)
+    xh, eh = torch.from_numpy(xnp).pin_memory(), torch.from_numpy(enp).pin_memory()
     x, emb = xh.to(dev), eh.to(dev)
     mask_h, masked_h = torch.empty_like(xh).pin_memory(), torch.empty_like(xh).pin_memory()
     prec = args.precision
@@ -215,13 +248,23 @@ def main():
         barrier()
         return ms
 
-    # ---- parity evidence: the timed precision against this repo's fp32 CUDA-core path (itself pinned to
-    # the oracle/golden vectors by tests/) on the first two utterances of the bench batch
+    # ---- parity evidence on utterances of the timed batch: the timed precision against (a) the CPU oracle
+    # (oracle/voicesplit_oracle.c, pinned to the reference's golden vectors; one utterance, rank 0 at N = 1 only) and
+    # (b) this repo's fp32 CUDA-core path on the first two utterances
     nb = min(2, B)
     ref32 = eng.forward(x[:nb], emb[:nb], precision="fp32")
     got = eng.forward(x[:nb], emb[:nb], precision=prec)
-    parity = {"vs": "fp32 CUDA-core path, first %d utterances" % nb, "mask_mae": float((got - ref32).abs().mean()),
-              "mask_max_abs": float((got - ref32).abs().max())}
+    parity = {"vs_fp32_path": {"utterances": nb, "mask_mae": float((got - ref32).abs().mean()), "mask_max_abs": float((got - ref32).abs().max())}}
+    if world == 1 and not args.no_extras:
+        try:
+            from oracle import oracle as c_oracle
+            t0 = time.perf_counter()
+            om = c_oracle.forward(sd, dims, xnp[:1], enp[:1])["mask"]
+            d = np.abs(got[:1].cpu().numpy() - om)
+            parity["vs_cpu_oracle"] = {"utterances": 1, "what": "utterance 0 of the timed batch, oracle/voicesplit_oracle.c (double accumulation)",
+                                       "mask_mae": float(d.mean()), "mask_max_abs": float(d.max()), "oracle_seconds": round(time.perf_counter() - t0, 2)}
+        except Exception as ex:      # noqa: BLE001
+            parity["vs_cpu_oracle"] = {"error": repr(ex)[:200]}
 
     # ---- device-resident throughput ("value")
     for _ in range(args.warmup):
@@ -266,56 +309,76 @@ def main():
     barrier()
     e2e_value, e2e_ms = vdist.aggregate_throughput(B * args.steps, local_e2e, dist, dev)
     clocks = sampler.stop() if rank == 0 else None
-    # ---- the single-pass fast mode, reported next to its measured error (never as the headline)
-    fast = None
-    if prec in ("fp16x3", "bf16x3", "fp16_f8c"):
-        fp = prec[:4]
-        gotf = eng.forward(x[:nb], emb[:nb], precision=fp)
-        for _ in range(2):
-            eng.forward(x, emb, precision=fp, want_masked=True)
-        fsteps = max(2, args.steps // 2)
-        fms = timed(lambda: eng.forward(x, emb, precision=fp, want_masked=True), fsteps)
-        fval, _ = vdist.aggregate_throughput(B * fsteps, fms, dist, dev)
-        fast = {"precision": fp, "value": fval, "unit": "utterances/s", "mask_mae_vs_fp32_path": float((gotf - ref32).abs().mean()),
-                "mask_max_abs_vs_fp32_path": float((gotf - ref32).abs().max()),
-                "note": "single MMA pass, 11-bit (fp16) / 8-bit (bf16) operands; error measured on stress weights"}
 
+    # ---- companion modes: the fp32-faithful fp16x3 (when the headline is fp16_f8c) and the single-pass fast mode, each with
+    # its measured error (never the headline)
+    def side_mode(p, note):
+        g = eng.forward(x[:nb], emb[:nb], precision=p)
+        for _ in range(2):
+            eng.forward(x, emb, precision=p, want_masked=True)
+        n = max(2, args.steps // 2)
+        ms = timed(lambda: eng.forward(x, emb, precision=p, want_masked=True), n)
+        v, _ = vdist.aggregate_throughput(B * n, ms, dist, dev)
+        return {"precision": p, "value": v, "unit": "utterances/s", "mask_mae_vs_fp32_path": float((g - ref32).abs().mean()),
+                "mask_max_abs_vs_fp32_path": float((g - ref32).abs().max()), "note": note}
+    fast = faithful = None
+    if prec in ("fp16x3", "bf16x3", "fp16_f8c"):
+        fast = side_mode(prec[:4], "single MMA pass, 11-bit (fp16) / 8-bit (bf16) operands; error measured on stress weights")
+    if prec == "fp16_f8c":
+        faithful = side_mode("fp16x3", "fp32-faithful split-fp16 mode (three fp16 MMA passes): the accuracy reference among the tensor-core modes")
+
+    del slots
+    line = None
     if rank == 0:
         peaks = load_peaks()
+        passes = PASS_EQUIV.get(prec)
         # dominant kernel: the five 5x5 dilated conv layers (89.5 % of the algorithmic FLOPs)
         conv_ms = [kernel_ms.get(f"cnn{i}") for i in (3, 4, 5, 6, 7)]
         roof = None
         if all(v is not None for v in conv_ms):
             avg = float(np.mean(conv_ms))
             ach = fl["conv5x5_layer"] * B / (avg / 1e3) / 1e12
-            passes = {"bf16x3": 3, "fp16x3": 3, "fp16_f8c": 2, "bf16": 1, "fp16": 1}.get(prec)
             peak = peaks["bf16_tflops_sustained"]
-            traffic = None
-            prof = os.path.join(ROOT, "profiles", "r01_conv_tc_summary.json")
-            if os.path.exists(prof) and passes:
-                pj = json.load(open(prof))
-                if pj.get("precision") == prec and pj.get("frames") == T and pj.get("freq_bins") == F:
-                    traffic = pj["dram_bytes_per_launch"] / pj["batch"] * B
+            traffic, traffic_src = None, None
+            for name in ("r02_conv_tc_summary.json", "r01_conv_tc_summary.json"):
+                prof = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(prof) and passes:
+                    pj = json.load(open(prof))
+                    if pj.get("precision") == prec and pj.get("frames") == T and pj.get("freq_bins") == F:
+                        traffic = pj["dram_bytes_per_launch"] / pj["batch"] * B
+                        traffic_src = f"profiles/{name} (ncu --set full at B = {pj['batch']}, scaled per utterance)"
+                        break
             roof = {"bound": "tensor", "kernel": "k_conv_tc: dilated 5x5 conv 64->64 + BN + act (cnn3..cnn7)", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01_conv_tc_summary.json (ncu --set full, scaled per utterance)" if traffic else None,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + ", sustained 16-bit dense (cuBLAS bf16; fp16 runs on the same pipe)",
                     "avg_launch_ms": avg, "algorithmic_flops_per_launch": fl["conv5x5_layer"] * B,
-                    "algorithmic_bytes_per_launch": B * T * padded_f(F) * 64 * 2 * (2 if passes >= 2 else 1) * 2 if passes else None,
-                    "mma_passes": passes, "tensor_pipe_frac_incl_passes": (ach * passes / peak) if passes else None,
-                    # what the tensor pipe actually executes: algorithmic flops x passes x 6/5 (five filter taps occupy six M=128 slots)
+                    "algorithmic_bytes_per_launch": B * T * padded_f(F) * 64 * 2 * (2 if (passes or 0) >= 2 else 1) * 2 if passes else None,
+                    "mma_pass_equivalents": passes, "tensor_pipe_frac_incl_passes": (ach * passes / peak) if passes else None,
+                    # what the tensor pipe actually executes: algorithmic flops x pass-equivalents x 6/5 (five filter taps occupy six M=128 slots)
                     "issued_tflops": (ach * passes * 1.2) if passes else None,
                     "issued_frac_of_peak": (ach * passes * 1.2 / peak) if passes else None,
                     "note": "fp32 mode runs on CUDA cores (no tensor pipe)" if prec == "fp32" else
-                            "frac counts ALGORITHMIC flops; the faithful mode issues 3 MMA passes (hi*hi + lo*hi + hi*lo) and pads 5 taps to 6 slots"}
-        line = {"metric": "utterances/s (601-frame, 257-bin spectrogram) masked", "value": value, "unit": "utterances/s",
+                            "frac counts ALGORITHMIC flops; fp16_f8c issues the fp16 pass + one e4m3 pass at twice the rate (2 pass-equivalents), "
+                            "fp16x3/bf16x3 three 16-bit passes; five taps occupy six M=128 slots"}
+        # the BiLSTM against the same tensor roofline (north_star: ">= 60 % of the BiLSTM tensor-core roofline")
+        roof_lstm = None
+        if kernel_ms.get("lstm_input_proj") and kernel_ms.get("lstm_recurrence"):
+            pj_ms, rc_ms = kernel_ms["lstm_input_proj"], kernel_ms["lstm_recurrence"]
+            peak = peaks["bf16_tflops_sustained"]
+            a_all = fl["lstm"] * B / ((pj_ms + rc_ms) / 1e3) / 1e12
+            a_pj = fl["lstm_input_proj"] * B / (pj_ms / 1e3) / 1e12
+            a_rc = fl["lstm_recurrence"] * B / (rc_ms / 1e3) / 1e12
+            roof_lstm = {"bound": "tensor (input projection) / step latency (recurrence)", "kernel": "k_gemm_tc<GATES> + k_lstm_tc",
+                         "achieved": a_all, "peak": peak, "unit": "TFLOP/s", "frac": a_all / peak,
+                         "input_projection": {"ms": pj_ms, "achieved": a_pj, "frac": a_pj / peak, "frac_incl_3_passes": 3 * a_pj / peak},
+                         "recurrence": {"ms": rc_ms, "achieved": a_rc, "frac": a_rc / peak, "us_per_step": rc_ms * 1e3 / T,
+                                        "note": "T sequential steps; bounded by the per-step exchange latency, not by the tensor pipe"},
+                         "algorithmic_flops_per_launch": fl["lstm"] * B,
+                         "ncu_tensor_pipe_pct": "profiles/r02_ncu_lstm_summary.txt / r01_ncu_gemm_summary.txt"}
+        line = {"metric": METRIC, "value": value, "unit": "utterances/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"bf16x3": "bf16x3 (split-bf16 operands hi+lo, 3 MMAs, fp32 accumulate)",
-                          "fp16x3": "fp16x3 (split-fp16 operands hi+lo, 3 MMAs, fp32 accumulate)",
-                          "fp16_f8c": "fp16 + e4m3 correction (conv: 4 f16 + 4 f8f6f4 MMAs per tap pair, fp32 accumulate; LSTM/FC fp16x3)",
-                          "bf16": "bf16", "fp16": "f16", "fp32": "f32"}[prec],
-                "data": "synthetic", "config": config,
+                "dtype": DTYPE[prec], "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "utterances/s", "ms_per_step": e2e_ms / args.steps,
                         "api": "vs_forward_host_submit/_wait (2 slots, copies overlap the neighbouring step's compute)",
                         "synchronous_call_value": sync_value,
@@ -323,131 +386,259 @@ def main():
                         "d2h_bytes_per_step": int(mask_h.numel() * 4 + masked_h.numel() * 4)},
                 "gpu_launches": launches_per_step * args.steps * 2,   # device-resident + e2e timed regions
                 "launches_per_step": launches_per_step,
-                "clocks": clocks, "roofline": roof, "parity": parity, "fast_mode": fast,
+                "clocks": clocks, "roofline": roof, "roofline_lstm": roof_lstm, "parity": parity, "faithful_mode": faithful, "fast_mode": fast,
                 "kernel_ms_last_step": {k: round(v, 4) for k, v in kernel_ms.items()},
                 "gflop_per_utt": {k: v / 1e9 for k, v in fl.items()},
                 "tflops_total_algorithmic": fl["total"] * value / 1e12}
-        if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_reference_throughput(dims, T, seconds_budget=20.0)
-            line["cpu_baseline"] = cb
+
+    # free the inference buffers before the secondary blocks
+    del eng, x, emb, xh, eh, mask_h, masked_h, ref32, got
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3]: training step, every N (so the scaling run carries the 1 -> 8 training curve)
+    if not args.no_extras and not args.no_train:
+        try:
+            tr = train_config4(dev, dist, rank, world, args.train_batch, barrier)
+        except Exception as ex:      # noqa: BLE001 - a failure here must not cost the headline
+            tr = {"error": repr(ex)[:300]}
+        if rank == 0:
+            line["train_config4"] = tr
+    if rank == 0:
         if world == 1 and not args.no_extras:
-            # secondary measurements (never the headline): BASELINE config 4 (training step) and config 5 (waveform in,
-            # separated waveform out) at the reference-native 301 x 601 shape; a failure here must not cost the headline
-            try:
-                del eng, x, emb, xh, eh, mask_h, masked_h, slots
-                torch.cuda.empty_cache()
-                line["extras"] = extra_measurements(dev)
-            except Exception as ex:      # noqa: BLE001
-                line["extras"] = {"error": repr(ex)[:300]}
+            for key, fn in (("config2_conv_stack_b64", lambda: config2_conv_stack(dev, prec)),
+                            ("stock_torch_gpu_baseline", lambda: stock_torch_gpu_baseline(dev, B, T)),
+                            ("other_precisions", lambda: other_precisions(dev, dims, B, T, prec)),
+                            ("extras", lambda: extra_measurements(dev))):
+                try:
+                    torch.cuda.empty_cache()
+                    line[key] = fn()
+                except Exception as ex:      # noqa: BLE001
+                    line[key] = {"error": repr(ex)[:300]}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_throughput(dims, T, runs=5, seconds_cap=60.0)
+            line["cpu_baseline"] = cb
         print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def extra_measurements(dev):
+# =====================================================================================================================
+def train_config4(dev, dist, rank, world, want_batch, barrier, steps=3, warmup=2):
+    """BASELINE configs[3]: forward (batch-statistics BatchNorm) + the reference's loss chain (train.py:95-108: both spectrograms
+    through the Q1-faithful differentiable iSTFT, Si-SNR, one fused engine call) + backward + ONE flat NCCL gradient
+    all-reduce (LSTM / FC tail overlapped with the conv backward) + Adam, at the reference-native 301 x 601, per-rank
+    BatchNorm statistics (the DDP default; SyncBN is a flag, tests/test_gpu_dp.py).  Per-GPU batch: `want_batch` halved
+    until the engine's workspace fits the free memory (agreed across ranks)."""
     from voicesplit_b200 import config as vconfig
-    from voicesplit_b200.engine import MaskEngine
+    from voicesplit_b200 import dist as vdist
     from voicesplit_b200.losses import SpecSiSNRLoss
     from models.voicesplit.model import VoiceSplit
-    out = {}
     dims = synth.make_dims(601, 256, 400, 600)
-
-    def timed(fn, n):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
-    # ---- config 4: forward (batch-stat BatchNorm) + loss chain of train.py:95-108 (both spectrograms through the Q1-faithful
-    # differentiable iSTFT, then Si-SNR) + backward + Adam, B = 32, 301 x 601
+    T, F = 301, 601
     model = VoiceSplit(vconfig.AttrDict(synth.make_config_dict(dims)))
     model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()})
     model = model.to(dev).train()
+    model.enable_data_parallel(dist, sync_bn=False, overlap=True)
+    eng = model.engine(dev)
+    free, _total = torch.cuda.mem_get_info(dev)
+    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    B = want_batch
+    while B > 1:
+        # engine workspace + the torch-side tensors of a step (x, target, phase, mask, mask*x, their gradients, loss chain) + slack
+        need = int(eng.lib.vs_train_workspace_bytes(eng.handle, B, T)) + 14 * B * T * F * 4 + (6 << 30)
+        if need <= free:
+            break
+        B //= 2
+    if dist is not None:
+        t = torch.tensor([B], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        B = int(t.item())
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    B, T, F = 32, 301, 601
-    x, emb = synth.make_inputs(B, T, dims, 7)
-    x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
+    x, emb = synth.make_inputs(min(B, 32), T, dims, 7 + rank)
+    reps = (B + x.shape[0] - 1) // x.shape[0]
+    x = torch.from_numpy(np.tile(x, (reps, 1, 1))[:B]).to(dev)
+    emb = torch.from_numpy(np.tile(emb, (reps, 1))[:B]).to(dev)
+    x = (x + 0.01 * torch.rand_like(x)).clamp_(0, 1)             # utterances differ (tiling only bounds the host-side generation time)
     target = torch.rand(B, T, F, device=dev) * x
     phase = (torch.rand(B, T, F, device=dev) * 2 - 1) * np.pi
     seq_len = torch.full((B, 1), 160 * (T - 1), device=dev, dtype=torch.int64)
-    crit = SpecSiSNRLoss(model.engine(dev), dict(n_fft=1200, hop_length=160, win_length=400), "q1")
+    crit = SpecSiSNRLoss(eng, dict(n_fft=1200, hop_length=160, win_length=400), "q1")
+    ar_events = []
 
-    def step():
+    def step(record=False):
         opt.zero_grad(set_to_none=True)
         mask = model(x, emb)
-        crit(mask * x, target, phase, seq_len).backward()
+        loss = crit(mask * x, target, phase, seq_len)
+        loss.backward()
+        if record:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+        n = vdist.allreduce_gradients(model, dist)
+        if record:
+            a1.record()
+            ar_events.append((a0, a1))
         opt.step()
-    step(); step()
-    ms = timed(step, 6)
-    out["train_step_config4"] = {"value": B / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "per_gpu_batch": B, "frames": T, "freq_bins": F,
-                                 "what": "forward (batch-stat BN) + differentiable iSTFT x2 + Si-SNR (one fused engine call) + backward + Adam; "
-                                         "conv fwd/dgrad/wgrad, LSTM input GEMMs and the iSTFT GEMMs on tcgen05 (fp16x3/bf16x3), rest fp32"}
-    del model, opt
+        return loss, n
+    for _ in range(warmup):
+        loss, nred = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, nred = step(record=True)
+    e1.record()
+    torch.cuda.synchronize()
+    local_ms = e0.elapsed_time(e1)
+    loss_val = float(loss)
+    ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events]))
+    barrier()
+    value, ms = vdist.aggregate_throughput(B * steps, local_ms, dist, dev)
+    ar_max = vdist.max_over_ranks(ar_ms, dist, dev)
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    out = {"value": value, "unit": "utterances/s", "frames_per_s": value * T, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "per_gpu_batch": B, "global_batch": B * world, "frames": T, "freq_bins": F, "n_gpus": world, "scaling": "weak",
+           "allreduce_ms": ar_max, "allreduce_elements": int(nred), "allreduce_bytes": int(nred) * 4,
+           "allreduce_what": "exposed time of allreduce_gradients after backward (max over ranks): waits for the LSTM/FC tail that was started "
+                             "mid-backward on NCCL's stream, then reduces the 2.3 MB conv/BatchNorm head; ReduceOp.AVG, no gather, no copy-back",
+           "bn_statistics": "per-rank (DDP default); sync_bn=True gives the concatenated-batch statistics of the single-process reference",
+           "loss_last_step": loss_val, "peak_memory_gib": round(peak_mem, 1),
+           "what": "forward (batch-stat BN) + differentiable iSTFT x2 + Si-SNR (one fused engine call) + backward + flat gradient all-reduce + Adam; "
+                   "conv fwd/dgrad/wgrad, LSTM input GEMMs and the iSTFT GEMMs on tcgen05 (fp16x3/bf16x3), BN / LSTM recurrence backward fp32 CUDA cores",
+           "flops_per_utt_algorithmic": 3 * flops_per_utt(T, F)["total"],
+           "tflops_algorithmic": 3 * flops_per_utt(T, F)["total"] * value / 1e12}
+    del model, opt, crit, x, emb, target, phase
     torch.cuda.empty_cache()
-    # ---- config 5: 3 s @ 16 kHz waveform -> STFT -> mask -> iSTFT -> waveform, B = 64
+    return out
+
+
+def _time_gpu(fn, n, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def config2_conv_stack(dev, prec, B=64, T=601, F=257):
+    """BASELINE configs[1]: the conv stack alone (8 x conv+BN+Mish and the transpose/view of model.py:70-74), B = 64, against the
+    reference's `model.conv` ops (oracle/torch_port.conv_stack: F.pad/conv2d/batch_norm/Mish -> cuDNN) on the SAME GPU."""
+    from oracle import torch_port
+    from voicesplit_b200.engine import MaskEngine
+    dims = synth.make_dims(F, 256, 400, 600)
+    sdn = synth.make_state_dict(dims, 0, "stress")
+    eng = MaskEngine(activation="mish", device=dev, **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).to(dev) for k, v in sdn.items() if v.dtype == np.float32})
+    x, _ = synth.make_inputs(B, T, dims, 21)
+    x = torch.from_numpy(x).to(dev)
+    sd = {k: torch.from_numpy(np.array(v)).to(dev) for k, v in sdn.items()}
+    out = {"batch": B, "frames": T, "freq_bins": F, "unit": "utterances/s", "gflop_per_utt": flops_per_utt(T, F)["conv"] / 1e9}
+    ref = torch_port.conv_stack(sd, x[:2])
+    for p in sorted({prec, "fp16x3"}):
+        got = eng.conv_stack(x[:2], precision=p)
+        ms = _time_gpu(lambda: eng.conv_stack(x, precision=p), 5)
+        out[p] = {"value": B / (ms / 1e3), "ms": ms, "tflops_algorithmic": flops_per_utt(T, F)["conv"] * B / (ms / 1e3) / 1e12,
+                  "max_abs_vs_stock_fp32": float((got - ref).abs().max()), "mean_abs_vs_stock_fp32": float((got - ref).abs().mean()),
+                  "ref_abs_max": float(ref.abs().max())}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32 in (("stock_fp32", False), ("stock_tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms = _time_gpu(lambda: torch_port.conv_stack(sd, x), 3)
+            out[name] = {"value": B / (ms / 1e3), "ms": ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["speedup_vs_stock_fp32"] = out[prec]["value"] / out["stock_fp32"]["value"]
+    out["speedup_vs_stock_tf32"] = out[prec]["value"] / out["stock_tf32"]["value"]
+    return out
+
+
+def stock_torch_gpu_baseline(dev, B=256, T=601, F=257):
+    """The honest GPU bar: the reference's own stock torch ops (restated in oracle/torch_port.py; the reference
+    tree cannot travel) on the SAME B200 through cuDNN/cuBLAS eager, strict fp32 and TF32-allowed, at the SAME per-GPU batch
+    as the headline (halved on out-of-memory, stated)."""
+    from oracle import torch_port
+    dims = synth.make_dims(F, 256, 400, 600)
+    sd = {k: torch.from_numpy(np.array(v)).to(dev) for k, v in synth.make_state_dict(dims, 0, "stress").items()}
+    res = {"frames": T, "freq_bins": F, "unit": "utterances/s", "requested_batch": B,
+           "what": "stock PyTorch eager (F.conv2d/batch_norm/Mish/LSTM/linear -> cuDNN/cuBLAS) on the same GPU, inputs resident"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        while B >= 1:
+            x = emb = None
+            try:
+                x, emb = synth.make_inputs(min(B, 32), T, dims, 11)
+                reps = (B + x.shape[0] - 1) // x.shape[0]
+                x = torch.from_numpy(np.tile(x, (reps, 1, 1))[:B]).to(dev)
+                emb = torch.from_numpy(np.tile(emb, (reps, 1))[:B]).to(dev)
+                for name, tf32 in (("fp32", False), ("tf32", True)):
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    torch.backends.cuda.matmul.allow_tf32 = tf32
+                    ms = _time_gpu(lambda: torch_port.forward(sd, x, emb), 3)
+                    res[name] = B / (ms / 1e3)
+                res["batch"] = B
+                break
+            except torch.OutOfMemoryError:
+                del x, emb
+                torch.cuda.empty_cache()
+                B //= 2
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return res
+
+
+def other_precisions(dev, dims, B, T, headline):
+    """BASELINE configs[2] names "fp32 and bf16": the same B = 256 forward in the fp32 CUDA-core mode and the bf16 modes."""
+    from voicesplit_b200.engine import MaskEngine
+    eng = MaskEngine(activation="mish", device=dev, **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(dims, 0, "stress").items() if v.dtype == np.float32})
+    x, emb = synth.make_inputs(B, T, dims, 1234)
+    x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
+    ref = eng.forward(x[:2], emb[:2], precision="fp32")
+    out = {"batch": B, "unit": "utterances/s"}
+    for p, n in (("fp32", 2), ("bf16x3", 3), ("bf16", 3)):
+        if p == headline:
+            continue
+        g = eng.forward(x[:2], emb[:2], precision=p)
+        ms = _time_gpu(lambda: eng.forward(x, emb, precision=p, want_masked=True), n, warm=1)
+        out[p] = {"value": B / (ms / 1e3), "ms_per_step": ms, "mask_mae_vs_fp32_path": float((g - ref).abs().mean()),
+                  "mask_max_abs_vs_fp32_path": float((g - ref).abs().max())}
+    return out
+
+
+def extra_measurements(dev):
+    """Config 5 (waveform in, separated waveform out) and d-vector extraction at the reference-native shape."""
+    from voicesplit_b200.engine import MaskEngine
+    out = {}
+    dims = synth.make_dims(601, 256, 400, 600)
     eng = MaskEngine(activation="mish", device=dev, **dims)
     eng.load_state_dict_tensors({k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(dims, 0, "stress").items() if v.dtype == np.float32})
     eng.configure_audio()
     Bw = 64
     wav = torch.randn(Bw, 48000, device=dev) * 0.05
     e2 = torch.randn(Bw, 256, device=dev)
-    ms = timed(lambda: eng.separate(wav, e2), 3)
+    ms = _time_gpu(lambda: eng.separate(wav, e2), 3, warm=1)
     out["audio_e2e_config5"] = {"value": Bw / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "batch": Bw, "samples": 48000,
                                 "what": "waveform -> STFT (tcgen05 GEMM) -> CNN+BiLSTM+FC mask (fp16x3) -> mask*spec -> iSTFT (mixture phase) -> waveform"}
-    # ---- d-vector extraction: 3 s reference clips -> GE2E embedding, B = 128
     from voicesplit_b200.speaker_encoder import SpeakerEncoder
     enc = SpeakerEncoder(engine=eng)
     enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_encoder_state_dict(1, "stress").items()})
     enc = enc.to(dev)
     ref_wav = torch.from_numpy(synth.make_reference_audio(128, 48000, 5)).to(dev)
-    ms = timed(lambda: enc.embed_wav(ref_wav), 5)
+    ms = _time_gpu(lambda: enc.embed_wav(ref_wav), 5, warm=1)
     out["dvector_extract"] = {"value": 128 / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "batch": 128, "samples": 48000,
                               "what": "waveform -> |STFT|^2 -> 40 mel -> log10 -> 6 windows x 3 x LSTM(768) (fp16x3 tcgen05, persistent recurrent "
                                       "kernel) -> Linear(256) -> L2 normalise -> mean"}
-    del eng, wav, e2, enc, ref_wav
-    torch.cuda.empty_cache()
-    # ---- the honest GPU bar: the reference's own stock torch ops (restated in oracle/torch_port.py; the
-    # reference tree cannot travel) on the SAME B200 through cuDNN/cuBLAS eager, strict fp32 and TF32-allowed
-    out["stock_torch_gpu_baseline"] = stock_torch_gpu_baseline(dev)
     return out
-
-
-def stock_torch_gpu_baseline(dev, B=32, T=601):
-    from oracle import torch_port
-    dims = synth.make_dims(257, 256, 400, 600)
-    sd = {k: torch.from_numpy(np.array(v)).to(dev) for k, v in synth.make_state_dict(dims, 0, "stress").items()}
-    x, emb = synth.make_inputs(B, T, dims, 11)
-    x, emb = torch.from_numpy(x).to(dev), torch.from_numpy(emb).to(dev)
-    res = {"batch": B, "frames": T, "freq_bins": 257, "unit": "utterances/s",
-           "what": "stock PyTorch eager (F.conv2d/batch_norm/Mish/LSTM/linear -> cuDNN/cuBLAS) on the same GPU, inputs resident"}
-    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
-    torch.backends.cudnn.benchmark = True
-    try:
-        for name, tf32 in (("fp32", False), ("tf32", True)):
-            torch.backends.cudnn.allow_tf32 = tf32
-            torch.backends.cuda.matmul.allow_tf32 = tf32
-            for _ in range(2):
-                torch_port.forward(sd, x, emb)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                torch_port.forward(sd, x, emb)
-            e1.record()
-            torch.cuda.synchronize()
-            res[name] = B * 3 / (e0.elapsed_time(e1) / 1e3)
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
-    return res
-
-
-def padded_f(F):
-    return (F + 2 + 7) // 8 * 8
 
 
 if __name__ == "__main__":

@@ -259,29 +259,67 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                             }
                         }
                     } else if (EPI == GEPI_FC1) {
+                        if (c0 + 32 <= a.n_tile && nbase + 32 <= a.ld16) {
+                            // a whole 32-column chunk of this row: 64 contiguous bytes per plane -> four 16-byte stores (columns
+                            // N..ld16 are row padding the consumer's TMA never reads past K = N: zeros there are harmless)
+                            __align__(16) elt16 vh[32], vl[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = nbase + j;
-                            if (n < a.N && c0 + j < a.n_tile) {
-                                float v = fmaxf(acc[i][j] + a.bias[n], 0.f);
-                                elt16 vh, vl;
-                                split16<ELT>(v, vh, vl);
-                                a.out_hi[(size_t)m * a.ld16 + n] = vh;
-                                if (a.out_lo) a.out_lo[(size_t)m * a.ld16 + n] = vl;
+                            for (int j = 0; j < 32; ++j) {
+                                const int n = nbase + j;
+                                const float v = n < a.N ? fmaxf(acc[i][j] + a.bias[n], 0.f) : 0.f;
+                                split16<ELT>(v, vh[j], vl[j]);
                             }
-                        }
-                    } else {
+                            uint4* dh = reinterpret_cast<uint4*>(a.out_hi + (size_t)m * a.ld16 + nbase);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = nbase + j;
-                            if (n < a.N && c0 + j < a.n_tile) {
-                                float v = sigmoid_f(acc[i][j] + a.bias[n]);
-                                const size_t o = (size_t)m * a.ld_out + n;
-                                a.out32[o] = v;
-                                if (a.masked) a.masked[o] = a.xmul[o] * v;
+                            for (int q = 0; q < 4; ++q) dh[q] = reinterpret_cast<const uint4*>(vh)[q];
+                            if (a.out_lo) {
+                                uint4* dl = reinterpret_cast<uint4*>(a.out_lo + (size_t)m * a.ld16 + nbase);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) dl[q] = reinterpret_cast<const uint4*>(vl)[q];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int n = nbase + j;
+                                if (n < a.N && c0 + j < a.n_tile) {
+                                    float v = fmaxf(acc[i][j] + a.bias[n], 0.f);
+                                    elt16 vh, vl;
+                                    split16<ELT>(v, vh, vl);
+                                    a.out_hi[(size_t)m * a.ld16 + n] = vh;
+                                    if (a.out_lo) a.out_lo[(size_t)m * a.ld16 + n] = vl;
+                                }
                             }
                         }
                     }
+                }
+            }
+            if (EPI == GEPI_FC2) {
+                // mask = sigmoid(acc + b), masked = x * mask.  A thread owns one ROW of the tile, but rows of the [M][F] outputs
+                // are F floats apart (F odd: no vector stores): transpose each 32 x 32 chunk through shared memory so that a
+                // warp instruction covers 32 consecutive columns of ONE row (128 contiguous bytes) for the x load and both stores
+                float* tr = reinterpret_cast<float*>(tmem_slot + 4) + (size_t)(warp - 2) * (32 * 33);
+                const int m0 = mb * 128 + quad * 32;
+#pragma unroll
+                for (int i = 0; i < kMaxCols; ++i) {
+                    const int c0 = cgrp * 32 + i * kColStep;
+                    if (c0 >= a.n_tile) continue;
+                    const int nbase = n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nbase + j;
+                        tr[lane * 33 + j] = sigmoid_f(acc[i][j] + (n < a.N ? a.bias[n] : 0.f));
+                    }
+                    __syncwarp();
+                    const int n = nbase + lane;
+                    if (n < a.N && c0 + lane < a.n_tile) {
+                        for (int r = 0; r < 32 && m0 + r < a.M; ++r) {
+                            const float v = tr[r * 33 + lane];
+                            const size_t o = (size_t)(m0 + r) * a.ld_out + n;
+                            a.out32[o] = v;
+                            if (a.masked) a.masked[o] = a.xmul[o] * v;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -443,10 +481,12 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     }
     const int w_bytes_al = (a.n_tile * 128 + 1023) & ~1023;
     const int stage_bytes = (a.passes == 3 ? 2 : 1) * (128 * 128 + w_bytes_al);
-    a.stages = (g->max_smem - 1024 - 512) / stage_bytes;
+    // FC2: 8 epilogue warps x (32 x 33) floats of transposition scratch behind the barriers
+    const int epi_scratch = epi == GEPI_FC2 ? kGemmEpiWarps * 32 * 33 * 4 : 0;
+    a.stages = (g->max_smem - 1024 - 512 - epi_scratch) / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     if (a.stages < 2) { set_error("gemm tile does not fit shared memory"); return VS_ERR_UNSUPPORTED; }
-    const int smem = 1024 + a.stages * stage_bytes + 512;
+    const int smem = 1024 + a.stages * stage_bytes + 512 + epi_scratch;
     const int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
     cudaError_t ce = cudaSuccess;
 #define VS_GEMM_TC(E, L)                                                                                   \

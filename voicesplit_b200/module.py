@@ -256,20 +256,17 @@ class MaskEstimator(nn.Module):
 
     def flat_gradient(self):
         """The flat fp32 buffer all current .grad tensors are views of, or None (e.g. gradients were accumulated or replaced)."""
-        f = self._flat_active
-        if f is None:
-            return None
         from .engine import MaskEngine
         names = dict(self.named_parameters())
         lay, total = MaskEngine.grad_layout({k: tuple(p.shape) for k, p in names.items()})
-        if f.numel() != total:
-            return None
-        base = f.data_ptr()
-        for k, (o, _n) in lay.items():
-            g = names[k].grad
-            if g is None or g.data_ptr() != base + 4 * o or not g.is_contiguous():
-                return None
-        return f
+        for f in self._flat:       # either buffer: an accumulated gradient stays in the buffer of the first backward
+            if f is None or f.numel() != total:
+                continue
+            base = f.data_ptr()
+            if all(names[k].grad is not None and names[k].grad.data_ptr() == base + 4 * o and names[k].grad.is_contiguous()
+                   for k, (o, _n) in lay.items()):
+                return f
+        return None
 
     def _guard(self, x):
         if not x.is_cuda:
