@@ -46,3 +46,19 @@ def test_wav2spec_spec2wav_pipeline():
     back = ao.spec2wav(S, ph)
     # normalisation clips below -100 dB relative to the reference level: reconstruction is exact up to that floor
     assert np.abs(back - y[:len(back)]).max() < 1e-4
+
+
+def test_real_audio_fixtures_are_reproducible_from_the_oracles():
+    """tests/golden/audio_demo_*.npz (real clips of the reference's demo set): the stored spectrogram rows are what the audio
+    oracle computes from the stored int16 mixture - fixture and oracle stay in step."""
+    import glob
+    import os
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "audio_demo_*.npz")))
+    assert len(paths) == 3
+    for p in paths:
+        z = np.load(p)
+        assert z["mix"].dtype == np.int16 and len(z["mix"]) == 48000 and len(z["ref"]) >= 16000
+        S, _ = ao.wav2spec(z["mix"].astype(np.float32) / 32768.0)
+        assert S.shape == (301, 601)
+        assert np.abs(S[z["row_idx"]] - z["spec_rows"]).max() < 1e-5
+        assert float(np.abs(z["dvec"]).max()) <= 1.0 and abs(float(np.linalg.norm(z["dvec"])) - 1.0) < 0.2   # mean of unit vectors

@@ -25,7 +25,7 @@ def _signals(B, L, seed=0):
 def engine():
     dims = synth.make_dims(601, 256, 400, 600)
     eng = MaskEngine(activation="mish", **dims)
-    sd = synth.make_state_dict(dims, 3, "default")
+    sd = synth.make_state_dict(dims, 3, "stress")
     eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
     eng.configure_audio()
     return eng
@@ -80,7 +80,7 @@ def test_separation_matches_full_oracle_pipeline(engine):
     Si-SNR of our output w.r.t. the oracle's output (the reference's own quality measure)."""
     from oracle import torch_port
     dims = synth.make_dims(601, 256, 400, 600)
-    sd = synth.make_state_dict(dims, 3, "default")
+    sd = synth.make_state_dict(dims, 3, "stress")
     wav = _signals(1, 20000, seed=11)
     emb = np.random.default_rng(2).standard_normal((1, 256)).astype(np.float32)
     got = engine.separate(torch.from_numpy(wav).cuda(), torch.from_numpy(emb).cuda()).cpu().numpy()[0]
@@ -100,7 +100,7 @@ def test_separation_from_reference_audio_matches_full_oracle_pipeline(engine):
     from oracle import encoder_oracle as eo, torch_port
     from voicesplit_b200.speaker_encoder import SpeakerEncoder
     dims = synth.make_dims(601, 256, 400, 600)
-    sd = synth.make_state_dict(dims, 3, "default")
+    sd = synth.make_state_dict(dims, 3, "stress")
     esd = synth.make_encoder_state_dict(4, "default")
     enc = SpeakerEncoder(engine=engine)
     enc.load_state_dict({k: torch.from_numpy(v) for k, v in esd.items()})

@@ -16,7 +16,7 @@ def model():
     from models.voicesplit.model import VoiceSplit
     dims = synth.make_dims(601, 256, 400, 600)
     m = VoiceSplit(vconfig.AttrDict(synth.make_config_dict(dims)))
-    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 3, "default").items()})
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 3, "stress").items()})
     return m.cuda().eval()
 
 
@@ -90,7 +90,7 @@ def test_validation_driver_matches_item_by_item_oracle_evaluation(model):
     mean_loss, mean_sdr = evaluate.validation(None, ap, model, loader, None, 0, cuda=True, loss_name="si_snr", test=True, batch_size=4, stats=stats)
     assert stats["items"] == 5 and stats["batches"] == 2 and stats["length_mismatch"] == 0
     dims = synth.make_dims(601, 256, 400, 600)
-    sd = synth.make_state_dict(dims, 3, "default")
+    sd = synth.make_state_dict(dims, 3, "stress")
     ref_losses, ref_sdrs = [], []
     for (emb, cs, ms, clean, mixed, mp, seq_len), in loader:
         mask = torch_port.forward(sd, ms[None].numpy(), emb[None].numpy(), "mish").numpy()[0]
@@ -111,7 +111,7 @@ def test_fast_si_snr_sweep_matches_fused_loss(model):
     batched = [tuple(torch.stack([it[0][j] for it in loader]) for j in range(7))]           # one batch of 3, as a DataLoader would collate
     got = evaluate.test_fast_with_si_srn(None, ap, model, batched)
     dims = synth.make_dims(601, 256, 400, 600)
-    sd = synth.make_state_dict(dims, 3, "default")
+    sd = synth.make_state_dict(dims, 3, "stress")
     emb, cs, ms, _, _, mp, seq_len = batched[0]
     mask = torch_port.forward(sd, ms.numpy(), emb.numpy(), "mish").numpy()
     want = loss_oracle.loss_and_grad(mask * ms.numpy(), cs.numpy(), mp.numpy(), seq_len.reshape(-1).numpy(), 1200, 160, 400, mode="q1")["loss"]
