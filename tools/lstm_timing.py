@@ -1,4 +1,5 @@
 import ctypes, os, sys
+os.environ["VOICESPLIT_LSTM_TIMING"] = "1"   # compile-time timers are off in the product kernel
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from voicesplit_b200 import synth

@@ -29,8 +29,18 @@ class DeviceAudioProcessor:
 
     get_spec_from_audio = wav2spec
 
-    def spec2wav(self, spectrogram: torch.Tensor, phase: torch.Tensor):
-        """(masked) spectrogram [B, T, F] + phasor from wav2spec -> waveform [B, hop * (T - 1)]."""
+    def spec2wav(self, spectrogram, phase=None):
+        """(masked) spectrogram [B, T, F] + phasor from wav2spec -> waveform [B, hop * (T - 1)].
+        The reference's drivers call this per item with NUMPY arrays and the phase ANGLE (validation(),
+        utils/generic_utils.py:499-504: `ap.inv_spectrogram(est_mag, phase=mixed_phase)`): a numpy spectrogram [T, F] with a
+        numpy angle array is accepted too and returns a numpy waveform, like openVoiceFilterAudioProcessor.spec2wav."""
+        if not isinstance(spectrogram, torch.Tensor):
+            import numpy as np
+            if phase is None:
+                raise ValueError("the device back end reconstructs with the mixture phase (Griffin-Lim is not provided)")
+            S = torch.as_tensor(np.asarray(spectrogram, dtype=np.float32), device=self.engine.device)
+            ang = torch.as_tensor(np.asarray(phase, dtype=np.float32), device=self.engine.device)
+            return self.spec2wav(S, torch.stack((torch.cos(ang), torch.sin(ang)), dim=-1)).cpu().numpy()
         single = spectrogram.dim() == 2
         w = self.engine.spec2wav(spectrogram[None] if single else spectrogram, phase[None] if single else phase)
         return w[0] if single else w

@@ -132,58 +132,70 @@ __global__ void __launch_bounds__(192, 1) k_lstm_uni_tc(const EncLstmArgs a, con
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // producer / issuer warps: the whole warp runs the warp-uniform loops, polls and waits; one elected lane issues the TMA /
+    // tcgen05 instructions (an `if (lane == 0)` region wraps each of them in an elect-and-loop sequence of ~100 cycles)
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- producer: W slice once, then h K-blocks every step ----------------
+        // ---------------- producer: W slice once, then h K-blocks every step ----------------
+        if (elect_one()) {
             mbar_arrive_expect_tx(w_full, (uint32_t)(2 * a.nkb * 4096));
             for (int p = 0; p < 2; ++p)
                 for (int kb = 0; kb < a.nkb; ++kb)
                     tma_load_2d(w_smem + (size_t)(p * a.nkb + kb) * 4096, p == 0 ? &tm_w_hi : &tm_w_lo, w_full, kb * 64, slice * 32);
-            int st = 0, ph = 0;
-            for (int s = 1; s < a.S; ++s) {
-                const unsigned int target = (unsigned int)s * a.nslices;     // every slice of the group has published h_{s-1}
-                unsigned int spins = 0;
-                while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
-                    if (++spins > (1u << 28)) __trap();
-                }
-                __threadfence();
-                asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy flag read -> async-proxy (TMA) data reads
-                const int row0 = ((s - 1) & 1) * a.Np + grp * kEB;
-                for (int kb = 0; kb < a.nkb; ++kb) {
-                    mbar_wait(&a_empty[st], ph ^ 1);
+        }
+        __syncwarp();
+        int st = 0, ph = 0;
+        for (int s = 1; s < a.S; ++s) {
+            const unsigned int target = (unsigned int)s * a.nslices;     // every slice of the group has published h_{s-1}
+            unsigned int spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+                if (++spins > (1u << 28)) __trap();
+            }
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy flag read -> async-proxy (TMA) data reads
+            const int row0 = ((s - 1) & 1) * a.Np + grp * kEB;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(&a_empty[st], ph ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[st], (uint32_t)stage_bytes);
                     uint8_t* dst = a_ring + (size_t)st * stage_bytes;
                     tma_load_2d(dst, &tm_h_hi, &a_full[st], kb * 64, row0);
                     tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
-                    if (++st == kEStages) { st = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++st == kEStages) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            const uint32_t idesc = make_idesc_bf16(128, 32, 1);
-            mbar_wait(w_full, 0);
-            tc_fence_after();
-            const uint32_t w_addr = smem_u32(w_smem);
-            int st = 0, ph = 0;
-            for (int s = 1; s < a.S; ++s) {
-                uint32_t accumulate = 0;
-                for (int kb = 0; kb < a.nkb; ++kb) {
-                    mbar_wait(&a_full[st], ph);
-                    tc_fence_after();
-                    const uint32_t h_hi = smem_u32(a_ring + (size_t)st * stage_bytes), h_lo = h_hi + 16384;
-                    const uint32_t w_hi = w_addr + (uint32_t)kb * 4096, w_lo = w_addr + (uint32_t)(a.nkb + kb) * 4096;
-                    for (int k = 0; k < 4 && kb * 4 + k < a.nk16; ++k) {
-                        umma_bf16(tmem, make_smem_desc(h_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
-                        accumulate = 1;
-                        umma_bf16(tmem, make_smem_desc(h_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
-                        umma_bf16(tmem, make_smem_desc(h_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = make_idesc_bf16(128, 32, 1);
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        const uint32_t w_addr = smem_u32(w_smem);
+        int st = 0, ph = 0;
+        for (int s = 1; s < a.S; ++s) {
+            uint32_t accumulate = 0;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(&a_full[st], ph);
+                tc_fence_after();
+                const uint32_t h_hi = smem_u32(a_ring + (size_t)st * stage_bytes), h_lo = h_hi + 16384;
+                const uint32_t w_hi = w_addr + (uint32_t)kb * 4096, w_lo = w_addr + (uint32_t)(a.nkb + kb) * 4096;
+                if (elect_one()) {
+                    const uint64_t d_hh = make_smem_desc(h_hi, 16, 1024, 2), d_hl = make_smem_desc(h_lo, 16, 1024, 2);
+                    const uint64_t d_wh = make_smem_desc(w_hi, 16, 1024, 2), d_wl = make_smem_desc(w_lo, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (kb * 4 + k < a.nk16) {
+                            umma_bf16(tmem, d_hh + 2 * k, d_wh + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                            umma_bf16(tmem, d_hl + 2 * k, d_wh + 2 * k, idesc, 1);
+                            umma_bf16(tmem, d_hh + 2 * k, d_wl + 2 * k, idesc, 1);
+                        }
                     }
                     umma_commit(&a_empty[st]);
-                    if (++st == kEStages) { st = 0; ph ^= 1; }
+                    if (kb == a.nkb - 1) umma_commit(acc_full);
                 }
-                umma_commit(acc_full);
+                __syncwarp();
+                accumulate = 1;
+                if (++st == kEStages) { st = 0; ph ^= 1; }
             }
         }
     } else {

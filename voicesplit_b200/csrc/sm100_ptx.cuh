@@ -84,6 +84,12 @@ __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatil
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1)

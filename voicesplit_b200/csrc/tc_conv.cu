@@ -53,6 +53,10 @@ struct ConvTcArgs {
     int f8c;              // VS_PREC_FP16_F8C: second plane = e4m3 correction operands, 4 f16 + 4 f8f6f4 MMAs per tap pair
     int strip_rows, box_rows, n_boxes, s_stages;
     int csz, n_iter;      // cluster size sharing the weight fetches; tile iterations every CTA runs (the same for all: lock step)
+    // 2-D tiles for the kw = 1 layer (cnn2, 7 taps along T): a tile is `tr` frames x 8 bins (N = 8 tr pixels), its input strip the
+    // (tr + kh - 1) x 8 block around it, loaded ONCE per plane with a 4-D TMA box and shared by all kh taps: tap dt is the window
+    // starting dt * 8 rows (= dt swizzle atoms) into the strip.  Flat tiles would fetch a fresh strip per tap (7x the bytes).
+    int tile2d, tr, n_ft, T;
     int act;
     const float* scale;
     const float* shift;
@@ -111,14 +115,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
     if (a.csz > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts onto them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int useful = a.N - 1;
+    const int useful = a.tile2d ? a.N : a.N - 1;     // flat tiles lose one pixel to the tap-pair shift
     // 3-pass modes: per tap row both strips (hi, lo) are resident; each weight tile is fetched once:
     // W_hi[j] multiplies S_hi and S_lo, W_lo[j] multiplies S_hi  (hi*hi + lo*hi + hi*lo).
     const int n_strip_loads = a.passes == 3 ? 2 : 1;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
+        // ===================== TMA producer =====================
+        // whole warp: warp-uniform loops and barrier waits; one elected lane arms the barrier and issues the TMA loads
+        {
             int ws = 0, wph = 0, ss = 0, sph = 0;
             const int slice_rows = 128 / a.csz;
             for (int itn = 0; itn < a.n_iter; ++itn) {
@@ -126,28 +131,47 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                 const bool valid = tile < a.total_tiles;    // a padding iteration still takes part in the shared weight stream
                 const int b = valid ? tile / a.tiles_per_utt : 0;
                 const int q0 = (tile - b * a.tiles_per_utt) * useful;
+                if (a.tile2d && valid) {      // one (tr + kh - 1) x 8 block per plane serves every tap of the tile
+                    const int tin = tile - b * a.tiles_per_utt, tt = tin / a.n_ft, ft = tin - tt * a.n_ft;
+                    for (int sp = 0; sp < n_strip_loads; ++sp) {
+                        mbar_wait(&s_empty[ss], sph ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
+                            tma_load_4d(s_ring + (size_t)ss * strip_bytes, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[ss], 0, ft * 8,
+                                        tt * a.tr - a.n_dt / 2, b);
+                        }
+                        __syncwarp();
+                        if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
+                    }
+                }
                 for (int dt = 0; dt < a.n_dt; ++dt) {
                     const int qs = q0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
-                    for (int sp = 0; valid && sp < n_strip_loads; ++sp) {  // strip planes of this tap row: hi (, lo)
+                    for (int sp = 0; valid && !a.tile2d && sp < n_strip_loads; ++sp) {  // strip planes of this tap row: hi (, lo)
                         mbar_wait(&s_empty[ss], sph ^ 1);
-                        mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
-                        uint8_t* dst = s_ring + (size_t)ss * strip_bytes;
-                        for (int i = 0; i < a.n_boxes; ++i)
-                            tma_load_3d(dst + (size_t)i * a.box_rows * 128, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[ss], 0,
-                                        qs + i * a.box_rows, b);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
+                            uint8_t* dst = s_ring + (size_t)ss * strip_bytes;
+                            for (int i = 0; i < a.n_boxes; ++i)
+                                tma_load_3d(dst + (size_t)i * a.box_rows * 128, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[ss], 0,
+                                            qs + i * a.box_rows, b);
+                        }
+                        __syncwarp();
                         if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
                     }
                     // weight tiles of this tap row: W_hi[j] (used against both strips), then W_lo[j]
                     for (int j = 0; j < a.n_j; ++j) {
                         for (int wp = 0; wp < n_strip_loads; ++wp) {
                             mbar_wait(&w_empty[ws], wph ^ 1);        // released by the MMA threads of all cluster members
-                            mbar_arrive_expect_tx(&w_full[ws], kWTileBytes);
-                            const void* tm = wp == 0 ? (const void*)&tm_w_hi : (const void*)&tm_w_lo;
-                            if (a.csz > 1)
-                                tma_load_2d_mc(w_ring + (size_t)ws * kWTileBytes + (size_t)crank * slice_rows * 128, tm, &w_full[ws], 0,
-                                               (dt * a.n_j + j) * 128 + (int)crank * slice_rows, cmask);
-                            else
-                                tma_load_2d(w_ring + (size_t)ws * kWTileBytes, tm, &w_full[ws], 0, (dt * a.n_j + j) * 128);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&w_full[ws], kWTileBytes);
+                                const void* tm = wp == 0 ? (const void*)&tm_w_hi : (const void*)&tm_w_lo;
+                                if (a.csz > 1)
+                                    tma_load_2d_mc(w_ring + (size_t)ws * kWTileBytes + (size_t)crank * slice_rows * 128, tm, &w_full[ws], 0,
+                                                   (dt * a.n_j + j) * 128 + (int)crank * slice_rows, cmask);
+                                else
+                                    tma_load_2d(w_ring + (size_t)ws * kWTileBytes, tm, &w_full[ws], 0, (dt * a.n_j + j) * 128);
+                            }
+                            __syncwarp();
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                     }
@@ -161,8 +185,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
+        // ===================== MMA issuer =====================
+        // The WHOLE warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues the tcgen05
+        // instructions.  Keeping the warp converged matters: tcgen05.mma / commit take their operands from uniform registers,
+        // and inside an `if (lane == 0)` region the compiler wraps every one of them in an elect-and-loop sequence that costs
+        // ~100 cycles per MMA - as much as the MMA itself (ncu source view, profiles/r02_ncu_conv_f8c_b256_summary.txt).
+        {
             const uint32_t idesc = make_idesc_bf16(128, a.N, ELT);
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
             int ws = 0, wph = 0, ss = 0, sph = 0, it = 0;
@@ -171,7 +199,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                     // padding iteration: no pixels, but the cluster's shared weight stages must still be consumed and released
                     for (int n = a.n_dt * a.n_j * n_strip_loads; n > 0; --n) {
                         mbar_wait(&w_full[ws], wph);
-                        if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
+                        if (elect_one()) { if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]); }
+                        __syncwarp();
                         if (++ws == kWStages) { ws = 0; wph ^= 1; }
                     }
                     continue;
@@ -182,15 +211,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)(buf * a.N);
                 uint32_t accumulate = 0;
+                uint32_t s_addr[2] = {0, 0};
+                int s_stage[2] = {0, 0};
                 for (int dt = 0; dt < a.n_dt; ++dt) {
-                    // strips of this tap row: hi in stage ss (, lo in the next stage)
-                    uint32_t s_addr[2];
-                    int s_stage[2];
-                    for (int sp = 0; sp < n_strip_loads; ++sp) {
-                        mbar_wait(&s_full[ss], sph);
-                        s_addr[sp] = smem_u32(s_ring + (size_t)ss * strip_bytes);
-                        s_stage[sp] = ss;
-                        if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
+                    // strips of this tap row: hi in stage ss (, lo in the next stage); 2-D tiles: one strip pair for all taps,
+                    // tap dt reads the window dt * 8 rows further down
+                    if (!a.tile2d || dt == 0) {
+                        for (int sp = 0; sp < n_strip_loads; ++sp) {
+                            mbar_wait(&s_full[ss], sph);
+                            s_addr[sp] = smem_u32(s_ring + (size_t)ss * strip_bytes);
+                            s_stage[sp] = ss;
+                            if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
+                        }
+                    } else {
+                        for (int sp = 0; sp < n_strip_loads; ++sp) s_addr[sp] += 8 * 128;
                     }
                     tc_fence_after();
                     for (int j = 0; j < a.n_j; ++j) {
@@ -198,39 +232,42 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                             mbar_wait(&w_full[ws], wph);
                             tc_fence_after();
                             const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWTileBytes);
-                            if (F8C) {
-                                // wp 0: W_hi x S_hi as four kind::f16 MMAs (K = 16); wp 1: the e4m3 correction tile x the c8 strip as
-                                // four kind::f8f6f4 MMAs (K = 32 bytes each): x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
-                                const uint32_t b_addr = s_addr[wp] + (uint32_t)(2 * j) * 128;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (wp == 0)
-                                        umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
-                                                  idesc, accumulate);
-                                    else
-                                        umma_f8(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
-                                                idesc8, 1);
-                                    accumulate = 1;
-                                }
-                            } else {
-                                const int n_sp = (wp == 0) ? n_strip_loads : 1;
-                                for (int sp = 0; sp < n_sp; ++sp) {
-                                    const uint32_t b_addr = s_addr[sp] + (uint32_t)(2 * j) * 128;
+                            // descriptors of K slice k = descriptor of slice 0 + 2k in the (address >> 4) field
+                            const uint64_t a_desc = make_smem_desc(w_addr, 16, 1024, 2);
+                            if (elect_one()) {
+                                if (F8C) {
+                                    // wp 0: W_hi x S_hi as four kind::f16 MMAs (K = 16); wp 1: the e4m3 correction tile x the c8 strip as
+                                    // four kind::f8f6f4 MMAs (K = 32 bytes each): x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
+                                    const uint64_t b_desc = make_smem_desc(s_addr[wp] + (uint32_t)(2 * j) * 128, 16, 1024, 2);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
-                                        umma_bf16(d_tmem, make_smem_desc(w_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2),
-                                                  idesc, accumulate);
-                                        accumulate = 1;
+                                        if (wp == 0) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                                        else umma_f8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1);
+                                    }
+                                } else {
+                                    const int n_sp = (wp == 0) ? n_strip_loads : 1;
+                                    for (int sp = 0; sp < n_sp; ++sp) {
+                                        const uint64_t b_desc = make_smem_desc(s_addr[sp] + (uint32_t)(2 * j) * 128, 16, 1024, 2);
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k == 0 && sp == 0) ? accumulate : 1u);
                                     }
                                 }
+                                if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
                             }
-                            if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
+                            __syncwarp();
+                            accumulate = 1;
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                     }
-                    for (int sp = 0; sp < n_strip_loads; ++sp) umma_commit(&s_empty[s_stage[sp]]);
+                    if (!a.tile2d || dt == a.n_dt - 1) {
+                        if (elect_one())
+                            for (int sp = 0; sp < n_strip_loads; ++sp) umma_commit(&s_empty[s_stage[sp]]);
+                        __syncwarp();
+                    }
                 }
-                umma_commit(&acc_full[buf]);
+                if (elect_one()) umma_commit(&acc_full[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -244,11 +281,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, aph = (it >> 1) & 1;
             const int b = tile / a.tiles_per_utt;
-            const int q0 = (tile - b * a.tiles_per_utt) * useful;
+            int q0 = (tile - b * a.tiles_per_utt) * useful;
+            int t0 = 0, f0 = 0;                          // 2-D tiles: first frame / bin; column p is frame t0 + p / 8, bin f0 + p % 8
+            if (a.tile2d) {
+                const int tin = tile - b * a.tiles_per_utt, tt = tin / a.n_ft;
+                t0 = tt * a.tr; f0 = (tin - tt * a.n_ft) * 8;
+                q0 = 0;
+            }
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
-            int f = (q0 + h + cgrp * 32) % a.Fp;         // frequency index of this lane's first pixel
+            int f = (q0 + h + cgrp * 32) % a.Fp;         // frequency index of this lane's first pixel (flat tiles)
             // 16-bit outputs: lanes L and L^2 hold channels co, co^1 of the same pixels; they swap every other value so that
             // each lane stores a CHANNEL PAIR (4 bytes per plane) of every second pixel instead of 2 bytes of every pixel
             const int codd = (lane >> 1) & 1;
@@ -274,22 +317,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                         const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
                         const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
                         const float acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
-                        y[i] = (f < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
+                        const int fcur = a.tile2d ? f0 + ((c0 + 2 * mm + h) & 7) : f;
+                        y[i] = (fcur < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
                         f += 2;
                         if (f >= a.Fp) f -= a.Fp;
                     }
                     if (OUT32) {
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
-                            const int p = c0 + 2 * (m + i) + h;
-                            if (p < useful && q0 + p < a.Q) o32[(size_t)p * 64] = y[i];
+                            int p = c0 + 2 * (m + i) + h;
+                            bool ok = p < useful && q0 + p < a.Q;
+                            if (a.tile2d) { ok = p < a.N && t0 + (p >> 3) < a.T; p = (t0 + (p >> 3)) * a.Fp + f0 + (p & 7); }
+                            if (ok) o32[(size_t)p * 64] = y[i];
                         }
                     } else {
                         // channel-even lane keeps the first pixel, channel-odd lane the second; each receives the partner channel
                         const float recv = __shfl_xor_sync(0xffffffffu, codd ? y[0] : y[1], 2);
                         const float v0 = codd ? recv : y[0], v1 = codd ? y[1] : recv;      // channels (co & ~1), (co | 1)
-                        const int p = c0 + 2 * (m + codd) + h;
-                        if (p < useful && q0 + p < a.Q) {
+                        int p = c0 + 2 * (m + codd) + h;
+                        bool ok = p < useful && q0 + p < a.Q;
+                        if (a.tile2d) { ok = p < a.N && t0 + (p >> 3) < a.T; p = (t0 + (p >> 3)) * a.Fp + f0 + (p & 7); }
+                        if (ok) {
                             if (F8C) {
                                 elt16 h0, h1;
                                 float l0, l1;
@@ -566,6 +614,7 @@ struct TcState {
     unsigned int* wmax = nullptr;
     int max_smem = 0;
     int cluster = 2;          // CTAs per cluster sharing the conv weight fetches (VOICESPLIT_CONV_CLUSTER = 1, 2, 4 or 8)
+    int tile2d = 1;           // 2-D tiles for the kw = 1 layer (VOICESPLIT_CONV_TILE2D = 0 falls back to flat tiles)
 };
 
 static int tile_n_for(const vs_engine*) { return 256; }
@@ -574,6 +623,7 @@ int tc_create(vs_engine* e) {
     TcState* s = new TcState();
     e->tc = s;
     cudaDeviceGetAttribute(&s->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+    if (const char* c = getenv("VOICESPLIT_CONV_TILE2D")) s->tile2d = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_CLUSTER")) {
         const int v = atoi(c);
         if (v == 1 || v == 2 || v == 4 || v == 8) s->cluster = v;
@@ -676,10 +726,20 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     a.passes = passes;
     a.f8c = call.f8c ? 1 : 0;
     if (call.f8c && (passes != 3 || !elt || call.out32 || !in_lo || !out_lo)) { set_error("fp16_f8c conv needs the fp16 hi + c8 plane pair"); return VS_ERR_INVALID; }
-    a.strip_rows = a.N + 8;
+    a.T = T;
+    // kw = 1 (cnn2): 2-D tiles of tr frames x 8 bins whose (tr + kh - 1) x 8 input block is loaded once for all kh taps
+    a.tile2d = (g.kw == 1 && g.dil == 1 && s->tile2d) ? 1 : 0;
+    if (a.tile2d) {
+        a.tr = 28;                                  // N = 224: two strip pairs of 34 x 8 rows + the weight ring fit shared memory
+        a.N = 8 * a.tr;
+        a.n_ft = Fp / 8;
+        a.tiles_per_utt = a.n_ft * ((T + a.tr - 1) / a.tr);
+        a.total_tiles = B * a.tiles_per_utt;
+    }
+    a.strip_rows = a.tile2d ? (a.tr + g.kh - 1) * 8 : a.N + 8;
     a.box_rows = a.strip_rows;
     a.n_boxes = 1;
-    while (a.box_rows > 256 || (a.box_rows % 8) != 0) {  // split the strip into equal boxes of a multiple of 8 rows
+    while (!a.tile2d && (a.box_rows > 256 || (a.box_rows % 8) != 0)) {  // split the strip into equal boxes of a multiple of 8 rows
         a.n_boxes++;
         if (a.strip_rows % a.n_boxes) { a.box_rows = 1000; continue; }
         a.box_rows = a.strip_rows / a.n_boxes;
@@ -700,8 +760,17 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
         uint64_t dims[3] = {64, (uint64_t)a.Q, (uint64_t)B};
         uint64_t str[2] = {128, (uint64_t)a.Q * 128};
         uint32_t box[3] = {64, (uint32_t)a.box_rows, 1};
-        bool ok = make_tmap_bf16(&tm_in_hi, (void*)in_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        ok = ok && make_tmap_bf16(&tm_in_lo, (void*)(in_lo ? in_lo : in_hi), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        bool ok;
+        if (a.tile2d) {   // [B][T][Fp][64]: box = 64 channels x 8 bins x (tr + kh - 1) frames; frames / bins outside the plane are zero-filled
+            uint64_t d4[4] = {64, (uint64_t)Fp, (uint64_t)T, (uint64_t)B};
+            uint64_t s4[3] = {128, (uint64_t)Fp * 128, (uint64_t)a.Q * 128};
+            uint32_t b4[4] = {64, 8, (uint32_t)(a.tr + g.kh - 1), 1};
+            ok = make_tmap_bf16(&tm_in_hi, (void*)in_hi, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_128B);
+            ok = ok && make_tmap_bf16(&tm_in_lo, (void*)(in_lo ? in_lo : in_hi), 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_128B);
+        } else {
+            ok = make_tmap_bf16(&tm_in_hi, (void*)in_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            ok = ok && make_tmap_bf16(&tm_in_lo, (void*)(in_lo ? in_lo : in_hi), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        }
         uint64_t wd[2] = {64, (uint64_t)a.n_dt * a.n_j * 128};
         uint64_t ws[1] = {128};
         uint32_t wb[2] = {64, 128};

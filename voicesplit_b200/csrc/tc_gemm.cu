@@ -62,12 +62,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // producer: whole warp waits (warp-uniform), one elected lane issues the TMA loads
             int st = 0, ph = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
                 for (int kb = 0; kb < a.n_kb; ++kb) {
                     mbar_wait(&empty[st], ph ^ 1);
+                    if (elect_one()) {
                     mbar_arrive_expect_tx(&full[st], (uint32_t)(nplanes * (a_bytes + w_bytes)));
                     uint8_t* dst = smem + (size_t)st * stage_bytes;
                     if (a.tn) {
@@ -87,15 +88,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                         tma_load_2d(dst + nplanes * a_bytes, &tm_w_hi, &full[st], kb * 64, nb * a.n_tile);
                         if (nplanes == 2) tma_load_2d(dst + nplanes * a_bytes + w_bytes_al, &tm_w_lo, &full[st], kb * 64, nb * a.n_tile);
                     }
+                    }
+                    __syncwarp();
                     if (++st == nst) { st = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // MMA issuer: the whole warp runs the warp-uniform control flow and waits, one elected lane issues (an `if (lane == 0)`
+        // region makes the compiler wrap every uniform-datapath instruction in an elect-and-loop sequence: ~100 cycles per MMA)
+        {
             // TN: both operands MN-major; K step = 16 rows of 128 B, the 64-column blocks are 8 KB apart (LBO)
             const uint32_t idesc = make_idesc_bf16(128, a.n_tile, ELT) | (a.tn ? ((1u << 15) | (1u << 16)) : 0u);
-            const uint32_t kstep = a.tn ? 2048u : 32u, lbo = a.tn ? 8192u : 16u;
+            const uint32_t kstep16 = a.tn ? (2048u >> 4) : (32u >> 4), lbo = a.tn ? 8192u : 16u;   // K step in descriptor address units
             int st = 0, ph = 0, cc = 0;   // cc: chunk counter across tiles (TMEM buffer = cc & 1)
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 for (int kb0 = 0; kb0 < a.n_kb; kb0 += kChunkKb, ++cc) {
@@ -110,19 +115,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                         tc_fence_after();
                         const uint32_t a_hi = smem_u32(smem + (size_t)st * stage_bytes), a_lo = a_hi + a_bytes;
                         const uint32_t w_hi = a_hi + nplanes * a_bytes, w_lo = w_hi + w_bytes_al;
+                        if (elect_one()) {
+                            const uint64_t d_ah = make_smem_desc(a_hi, lbo, 1024, 2), d_wh = make_smem_desc(w_hi, lbo, 1024, 2);
+                            const uint64_t d_al = make_smem_desc(a_lo, lbo, 1024, 2), d_wl = make_smem_desc(w_lo, lbo, 1024, 2);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, make_smem_desc(a_hi + k * kstep, lbo, 1024, 2), make_smem_desc(w_hi + k * kstep, lbo, 1024, 2), idesc, accumulate);
-                            accumulate = 1;
-                            if (nplanes == 2) {
-                                umma_bf16(d_tmem, make_smem_desc(a_lo + k * kstep, lbo, 1024, 2), make_smem_desc(w_hi + k * kstep, lbo, 1024, 2), idesc, 1);
-                                umma_bf16(d_tmem, make_smem_desc(a_hi + k * kstep, lbo, 1024, 2), make_smem_desc(w_lo + k * kstep, lbo, 1024, 2), idesc, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t o = (uint64_t)(k * kstep16);
+                                umma_bf16(d_tmem, d_ah + o, d_wh + o, idesc, k == 0 ? accumulate : 1u);
+                                if (nplanes == 2) {
+                                    umma_bf16(d_tmem, d_al + o, d_wh + o, idesc, 1);
+                                    umma_bf16(d_tmem, d_ah + o, d_wl + o, idesc, 1);
+                                }
                             }
+                            umma_commit(&empty[st]);
                         }
-                        umma_commit(&empty[st]);
+                        __syncwarp();
+                        accumulate = 1;
                         if (++st == nst) { st = 0; ph ^= 1; }
                     }
-                    umma_commit(&acc_full[buf]);
+                    if (elect_one()) umma_commit(&acc_full[buf]);
+                    __syncwarp();
                 }
             }
         }

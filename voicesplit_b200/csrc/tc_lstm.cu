@@ -13,6 +13,7 @@
 // The CTAs of one (direction, group) meet at that barrier once per step; nothing else is shared.
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace vs {
 using namespace ptx;
@@ -40,7 +41,10 @@ struct LstmTcArgs {
 // timing[4] cell thread 64: waiting for acc_full    timing[5] cell thread 64: TMEM load + gate math
 // timing[6] cell thread 64: stores                  timing[7] cell thread 64: bar.sync + fence + atomic
 
-template <int ELT>
+// TIMING: phase timers (clock64 around every wait / issue / store phase) for vs_debug_lstm_timing - compiled out of the product
+// kernel, enabled with VOICESPLIT_LSTM_TIMING=1 (tools/lstm_timing.py)
+#define VS_CLK() (TIMING ? clock64() : 0ll)
+template <int ELT, bool TIMING>
 __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __grid_constant__ CUtensorMap tm_w_hi,
                                                     const __grid_constant__ CUtensorMap tm_w_lo,
                                                     const __grid_constant__ CUtensorMap tm_h_hi,
@@ -83,24 +87,29 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- producer: W slice once, then h K-blocks every step ----------------
-            mbar_arrive_expect_tx(w_full, (uint32_t)(nplanes * a.nkb * 8192));
-            for (int p = 0; p < nplanes; ++p)
-                for (int kb = 0; kb < a.nkb; ++kb)
-                    tma_load_2d(w_smem + (size_t)(p * a.nkb + kb) * 8192, p == 0 ? &tm_w_hi : &tm_w_lo, w_full, kb * 64,
-                                (d * a.nslices + slice) * 64);
+        // ---------------- producer: W slice once, then h K-blocks every step ----------------
+        // the whole warp polls / waits (warp-uniform), one elected lane issues the TMA instructions (no per-instruction
+        // elect-and-loop sequences as inside an `if (lane == 0)` region)
+        {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(w_full, (uint32_t)(nplanes * a.nkb * 8192));
+                for (int p = 0; p < nplanes; ++p)
+                    for (int kb = 0; kb < a.nkb; ++kb)
+                        tma_load_2d(w_smem + (size_t)(p * a.nkb + kb) * 8192, p == 0 ? &tm_w_hi : &tm_w_lo, w_full, kb * 64,
+                                    (d * a.nslices + slice) * 64);
+            }
+            __syncwarp();
             int st = 0, ph = 0;
             long long tm_spin = 0, tm_issue = 0;
             for (int s = 1; s < a.T; ++s) {
                 // wait until every slice of this (direction, group) has published h_{s-1}
                 const unsigned int target = (unsigned int)s * a.nslices;
                 unsigned int spins = 0;
-                const long long c0 = clock64();
+                const long long c0 = VS_CLK();
                 while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
                     if (++spins > (1u << 28)) __trap();
                 }
-                const long long c1 = clock64();
+                const long long c1 = VS_CLK();
                 tm_spin += c1 - c0;
                 __threadfence();
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy flag read -> async-proxy (TMA) data reads
@@ -108,19 +117,22 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 const int row0 = ((d * 2 + par) * a.Bp) + grp * kLB;
                 for (int kb = 0; kb < a.nkb; ++kb) {
                     mbar_wait(&a_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&a_full[st], (uint32_t)stage_bytes);
-                    uint8_t* dst = a_ring + (size_t)st * stage_bytes;
-                    tma_load_2d(dst, &tm_h_hi, &a_full[st], kb * 64, row0);
-                    if (nplanes == 2) tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&a_full[st], (uint32_t)stage_bytes);
+                        uint8_t* dst = a_ring + (size_t)st * stage_bytes;
+                        tma_load_2d(dst, &tm_h_hi, &a_full[st], kb * 64, row0);
+                        if (nplanes == 2) tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
+                    }
+                    __syncwarp();
                     if (++st == kLStages) { st = 0; ph ^= 1; }
                 }
-                tm_issue += clock64() - c1;
+                tm_issue += VS_CLK() - c1;
             }
-            if (blockIdx.x == 0 && a.timing) { a.timing[0] = tm_spin; a.timing[1] = tm_issue; }
+            if (TIMING && blockIdx.x == 0 && lane == 0 && a.timing) { a.timing[0] = tm_spin; a.timing[1] = tm_issue; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
+        // ---------------- MMA issuer: whole warp waits, one elected lane issues ----------------
+        {
             const uint32_t idesc = make_idesc_bf16(128, 64, ELT);
             mbar_wait(w_full, 0);
             tc_fence_after();
@@ -130,28 +142,36 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
             for (int s = 1; s < a.T; ++s) {
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < a.nkb; ++kb) {
-                    const long long c0 = clock64();
+                    const long long c0 = VS_CLK();
                     mbar_wait(&a_full[st], ph);
-                    const long long c1 = clock64();
+                    const long long c1 = VS_CLK();
                     tm_wait += c1 - c0;
                     tc_fence_after();
                     const uint32_t h_hi = smem_u32(a_ring + (size_t)st * stage_bytes), h_lo = h_hi + 16384;
                     const uint32_t w_hi = w_addr + (uint32_t)kb * 8192, w_lo = w_addr + (uint32_t)(a.nkb + kb) * 8192;
-                    for (int k = 0; k < 4 && kb * 4 + k < a.nk16; ++k) {
-                        umma_bf16(tmem, make_smem_desc(h_hi + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, accumulate);
-                        accumulate = 1;
-                        if (nplanes == 2) {
-                            umma_bf16(tmem, make_smem_desc(h_lo + k * 32, 16, 1024, 2), make_smem_desc(w_hi + k * 32, 16, 1024, 2), idesc, 1);
-                            umma_bf16(tmem, make_smem_desc(h_hi + k * 32, 16, 1024, 2), make_smem_desc(w_lo + k * 32, 16, 1024, 2), idesc, 1);
+                    if (elect_one()) {
+                        const uint64_t d_hh = make_smem_desc(h_hi, 16, 1024, 2), d_hl = make_smem_desc(h_lo, 16, 1024, 2);
+                        const uint64_t d_wh = make_smem_desc(w_hi, 16, 1024, 2), d_wl = make_smem_desc(w_lo, 16, 1024, 2);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (kb * 4 + k < a.nk16) {
+                                umma_bf16(tmem, d_hh + 2 * k, d_wh + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                                if (nplanes == 2) {
+                                    umma_bf16(tmem, d_hl + 2 * k, d_wh + 2 * k, idesc, 1);
+                                    umma_bf16(tmem, d_hh + 2 * k, d_wl + 2 * k, idesc, 1);
+                                }
+                            }
                         }
+                        umma_commit(&a_empty[st]);
+                        if (kb == a.nkb - 1) umma_commit(acc_full);
                     }
-                    umma_commit(&a_empty[st]);
+                    __syncwarp();
+                    accumulate = 1;
                     if (++st == kLStages) { st = 0; ph ^= 1; }
-                    tm_mma += clock64() - c1;
+                    tm_mma += VS_CLK() - c1;
                 }
-                umma_commit(acc_full);
             }
-            if (blockIdx.x == 0 && a.timing) { a.timing[2] = tm_wait; a.timing[3] = tm_mma; }
+            if (TIMING && blockIdx.x == 0 && lane == 0 && a.timing) { a.timing[2] = tm_wait; a.timing[3] = tm_mma; }
         }
     } else {
         // ---------------- cell update: thread = one utterance, 16 units ----------------
@@ -183,11 +203,11 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     for (int j = 0; j < kLU; ++j) gx[g][j] = j < nu ? __ldg(gsrc + (size_t)g * a.H + j) : 0.f;
                 }
             }
-            long long c0 = clock64();
+            long long c0 = VS_CLK();
             if (s > 0) {
                 mbar_wait(acc_full, (s - 1) & 1);
-                tm_acc += clock64() - c0;
-                c0 = clock64();
+                tm_acc += VS_CLK() - c0;
+                c0 = VS_CLK();
                 tc_fence_after();
                 uint32_t r0[32], r1[32];
                 tmem_ld_32x32(t_base, r0);
@@ -218,7 +238,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 split16<ELT>(fmaxf(hv[j], 0.f), rh[j], rl[j]);
             }
             {
-                const long long c1 = clock64();
+                const long long c1 = VS_CLK();
                 tm_math += c1 - c0;
                 c0 = c1;
             }
@@ -254,7 +274,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 }
             }
             {
-                const long long c1 = clock64();
+                const long long c1 = VS_CLK();
                 tm_store += c1 - c0;
                 c0 = c1;
             }
@@ -267,10 +287,10 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     __threadfence();
                     atomicAdd(counter, 1u);
                 }
-                tm_bar += clock64() - c0;
+                tm_bar += VS_CLK() - c0;
             }
         }
-        if (blockIdx.x == 0 && threadIdx.x == 64 && a.timing) { a.timing[4] = tm_acc; a.timing[5] = tm_math; a.timing[6] = tm_store; a.timing[7] = tm_bar; }
+        if (TIMING && blockIdx.x == 0 && threadIdx.x == 64 && a.timing) { a.timing[4] = tm_acc; a.timing[5] = tm_math; a.timing[6] = tm_store; a.timing[7] = tm_bar; }
     }
     tc_fence_before();
     __syncthreads();
@@ -371,7 +391,9 @@ int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* ho
     }
     cudaError_t ce = cudaMemsetAsync(a.barrier, 0, 4096, st);
     if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return VS_ERR_CUDA; }
-    const void* fn = elt ? (const void*)k_lstm_tc<1> : (const void*)k_lstm_tc<0>;
+    static const bool timing = getenv("VOICESPLIT_LSTM_TIMING") && atoi(getenv("VOICESPLIT_LSTM_TIMING")) != 0;
+    const void* fn = timing ? (elt ? (const void*)k_lstm_tc<1, true> : (const void*)k_lstm_tc<0, true>)
+                            : (elt ? (const void*)k_lstm_tc<1, false> : (const void*)k_lstm_tc<0, false>);
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return VS_ERR_CUDA; }
     // groups of 128 utterances are independent: run as many as are co-resident per launch

@@ -59,25 +59,30 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(const WgradTcArgs a, const 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // producer / issuer: the whole warp runs the warp-uniform loops and waits, one elected lane issues the TMA / tcgen05
+    // instructions (inside an `if (lane == 0)` region every uniform-datapath instruction gets an elect-and-loop wrapper)
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int st = 0, ph = 0;
             for (int it = 0; it < my_chunks; ++it) {
                 const int c = idx + it * a.cpk;
                 const int b = c / a.chunks_per_utt, q0 = (c - b * a.chunks_per_utt) * kWgChunk;
                 const int qs = q0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
                 mbar_wait(&empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&full[st], (uint32_t)kWgStageBytes);
-                uint8_t* dst = smem + (size_t)st * kWgStageBytes;
-                tma_load_3d(dst, &tm_a_hi, &full[st], 0, qs, b);
-                tma_load_3d(dst + kWgStrip * 128, &tm_a_lo, &full[st], 0, qs, b);
-                tma_load_3d(dst + 2 * kWgStrip * 128, &tm_d_hi, &full[st], 0, q0, b);
-                tma_load_3d(dst + 2 * kWgStrip * 128 + kWgChunk * 128, &tm_d_lo, &full[st], 0, q0, b);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)kWgStageBytes);
+                    uint8_t* dst = smem + (size_t)st * kWgStageBytes;
+                    tma_load_3d(dst, &tm_a_hi, &full[st], 0, qs, b);
+                    tma_load_3d(dst + kWgStrip * 128, &tm_a_lo, &full[st], 0, qs, b);
+                    tma_load_3d(dst + 2 * kWgStrip * 128, &tm_d_hi, &full[st], 0, q0, b);
+                    tma_load_3d(dst + 2 * kWgStrip * 128 + kWgChunk * 128, &tm_d_lo, &full[st], 0, q0, b);
+                }
+                __syncwarp();
                 if (++st == kWgStages) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // bf16 operands, fp32 accumulate, A and B both MN-major
             const uint32_t idesc = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
             int st = 0, ph = 0;
@@ -92,21 +97,24 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(const WgradTcArgs a, const 
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + (size_t)st * kWgStageBytes), a_lo = a_hi + kWgStrip * 128;
                 const uint32_t d_hi = a_hi + 2 * kWgStrip * 128, d_lo = d_hi + kWgChunk * 128;
-                for (int pass = 0; pass < 3; ++pass) {      // hi*hi, lo*hi, hi*lo
-                    const uint32_t ap = pass == 1 ? a_lo : a_hi, dp = pass == 2 ? d_lo : d_hi;
-                    for (int j = 0; j < a.n_j; ++j) {
-                        const uint32_t d_tmem = tmem + (uint32_t)(buf * 256 + j * 64);
+                if (elect_one()) {
+                    for (int pass = 0; pass < 3; ++pass) {      // hi*hi, lo*hi, hi*lo
+                        const uint32_t ap = pass == 1 ? a_lo : a_hi, dp = pass == 2 ? d_lo : d_hi;
+                        for (int j = 0; j < a.n_j; ++j) {
+                            const uint32_t d_tmem = tmem + (uint32_t)(buf * 256 + j * 64);
+                            // K step = 16 pixel rows = 2048 bytes = 128 descriptor address units
+                            const uint64_t da0 = make_smem_desc(ap + (uint32_t)(2 * j) * 128, 128, 1024, 2);
+                            const uint64_t db0 = make_smem_desc(dp, 128, 1024, 2);
 #pragma unroll
-                        for (int k = 0; k < kWgChunk / 16; ++k) {
-                            const uint64_t da = make_smem_desc(ap + (uint32_t)(2 * j + 16 * k) * 128, 128, 1024, 2);
-                            const uint64_t db = make_smem_desc(dp + (uint32_t)(16 * k) * 128, 128, 1024, 2);
-                            umma_bf16(d_tmem, da, db, idesc, (first_of_group && pass == 0 && k == 0) ? 0u : 1u);
+                            for (int k = 0; k < kWgChunk / 16; ++k)
+                                umma_bf16(d_tmem, da0 + 128 * k, db0 + 128 * k, idesc, (first_of_group && pass == 0 && k == 0) ? 0u : 1u);
                         }
                     }
+                    umma_commit(&empty[st]);
+                    if ((it % kWgFlush) == kWgFlush - 1 || it == my_chunks - 1) umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&empty[st]);
+                __syncwarp();
                 if (++st == kWgStages) { st = 0; ph ^= 1; }
-                if ((it % kWgFlush) == kWgFlush - 1 || it == my_chunks - 1) umma_commit(&acc_full[buf]);
             }
         }
     } else {
