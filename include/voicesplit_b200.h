@@ -124,6 +124,11 @@ int vs_forward(vs_engine* e, const float* x, const float* emb, float* mask, floa
  * device staging area for this entry point, so repeated calls of the same shape do not allocate. */
 int vs_forward_host(vs_engine* e, const float* x_host, const float* emb_host, float* mask_host,
                     float* masked_host, int32_t B, int32_t T, int32_t precision, void* stream);
+/* The host entry points are the only forward calls that own device memory: the FIRST call with a larger (B, T, precision)
+ * than seen before does one cudaMalloc (after synchronising the stream) - every later call of that or a smaller shape
+ * allocates nothing.  vs_forward_host_reserve does that allocation up front (staging of vs_forward_host and both slots +
+ * the shared workspace of vs_forward_host_submit), so that a serving loop never allocates on a request. */
+int vs_forward_host_reserve(vs_engine* e, int32_t B, int32_t T, int32_t precision);
 
 /* Pipelined form of vs_forward_host for serving loops: two slots (0, 1), each with its own device
  * staging.  submit enqueues  H2D (copy stream) -> vs_forward (compute stream) -> D2H (copy stream)

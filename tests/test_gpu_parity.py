@@ -230,6 +230,7 @@ def test_pipelined_host_entry_matches_synchronous():
     sd = synth.make_state_dict(dims, 2, "stress")
     eng = MaskEngine(activation="mish", **dims)
     eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    eng.host_reserve(3, 26, "fp16x3")            # staging for every shape below is allocated here, not on a request
     bufs = []
     for i in range(2):
         x, emb = synth.make_inputs(3, 21 + 5 * i, dims, 40 + i)

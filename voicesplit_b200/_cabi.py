@@ -79,6 +79,7 @@ SIGNATURES = {
     "vs_forward_host": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "vs_forward_host_submit": (ctypes.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I]),
     "vs_forward_host_wait": (ctypes.c_int, [_VP, _I]),
+    "vs_forward_host_reserve": (ctypes.c_int, [_VP, _I, _I, _I]),
     "vs_engine_set_train_tensor_cores": (ctypes.c_int, [_VP, _I]),
     "vs_train_workspace_bytes": (_SZ, [_VP, _I, _I]),
     "vs_train_forward": (ctypes.c_int, [_VP, ctypes.POINTER(VsTrainState), _VP, _VP, _VP, _I, _I, _VP, _SZ, _VP]),

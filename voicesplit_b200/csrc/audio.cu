@@ -18,7 +18,7 @@ struct AudioState {
     int n_fft = 0, hop = 0, win = 0, bins = 0;
     float min_db = -100.f, ref_db = 20.f;
     elt16 *dft_hi = nullptr, *dft_lo = nullptr;     // [2 bins][win]           row 2k = w cos, 2k+1 = -w sin
-    elt16 *idft_hi = nullptr, *idft_lo = nullptr;   // [win][ldk = 2 bins pad] col 2k = c_k w cos / N, 2k+1 = -c_k w sin / N
+    elt16 *idft_hi = nullptr, *idft_lo = nullptr;   // [win][ldk = 2 bins pad] col 2k = c_k w cos, 2k+1 = -c_k w sin (x n_fft: 1 / n_fft in the overlap-add)
     float* wsq = nullptr;                           // [win] window squared
     int ldk = 0;
 };
@@ -43,7 +43,8 @@ __global__ void k_make_dft(int n_fft, int win, int bins, int ldk, elt16* dhi, el
         if (c < 2 * bins) {
             double ang = 2.0 * M_PI * ((long long)k * (lp + n) % n_fft) / n_fft;
             double ck = (k == 0 || 2 * k == n_fft) ? 1.0 : 2.0;       // one-sided spectrum: interior bins count twice
-            v = hann_p(n, win) * ck / n_fft * ((c & 1) ? -sin(ang) : cos(ang));
+            // stored x n_fft (1 / n_fft is applied by the overlap-add): keeps the fp16 `lo` halves out of the subnormal range
+            v = hann_p(n, win) * ck * ((c & 1) ? -sin(ang) : cos(ang));
         }
         split16<1>((float)v, ihi[i], ilo[i]);
     }
@@ -103,6 +104,7 @@ __global__ void k_overlap_add(const float* __restrict__ frames /*[B*T][win]*/, c
         int nidx = pos - t * hop;
         if (nidx >= 0 && nidx < win) { acc += frames[((size_t)b * T + t) * win + nidx]; wss += wsq[nidx]; }
     }
+    acc *= 0.5f / (float)half;                     // the inverse-DFT operand is stored x n_fft (k_make_dft); half = n_fft / 2
     out[i] = wss > 1.17549435e-38f ? acc / wss : acc;
 }
 

@@ -436,6 +436,39 @@ int vs_forward_host_submit(vs_engine* e, int32_t slot, const float* x_host, cons
     return VS_OK;
 }
 
+int vs_forward_host_reserve(vs_engine* e, int32_t B, int32_t T, int32_t precision) {
+    int rc = check_common(e, B, T, precision);
+    if (rc != VS_OK) return rc;
+    const size_t nx = (size_t)B * T * e->d.num_freq * sizeof(float), ne = (size_t)B * e->d.emb_dim * sizeof(float);
+    const size_t io_need = align_up(nx, 1024) * 3 + align_up(ne, 1024);
+    const size_t wsb = vs_workspace_bytes(e, B, T, precision);
+    if (io_need + wsb > e->stage_bytes) {
+        VS_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(e->stage);
+        e->stage = nullptr; e->stage_bytes = 0;
+        VS_CUDA_TRY(cudaMalloc(&e->stage, io_need + wsb));
+        e->stage_bytes = io_need + wsb;
+    }
+    HostPipe* p = nullptr;
+    rc = pipe_get(e, &p);
+    if (rc != VS_OK) return rc;
+    for (HostSlot& s : p->slot) {
+        if (s.busy) { set_error("a slot is in flight: wait for it before reserving"); return VS_ERR_STATE; }
+        if (io_need > s.io_bytes) {
+            cudaFree(s.io); s.io = nullptr; s.io_bytes = 0;
+            VS_CUDA_TRY(cudaMalloc(&s.io, io_need));
+            s.io_bytes = io_need;
+        }
+    }
+    if (wsb > p->ws_bytes) {
+        VS_CUDA_TRY(cudaStreamSynchronize(p->compute));
+        cudaFree(p->ws); p->ws = nullptr; p->ws_bytes = 0;
+        VS_CUDA_TRY(cudaMalloc(&p->ws, wsb));
+        p->ws_bytes = wsb;
+    }
+    return VS_OK;
+}
+
 int vs_forward_host_wait(vs_engine* e, int32_t slot) {
     if (!e || !e->pipe || slot < 0 || slot > 1) { set_error("nothing submitted on this slot"); return VS_ERR_STATE; }
     HostSlot& s = ((HostPipe*)e->pipe)->slot[slot];

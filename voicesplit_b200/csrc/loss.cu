@@ -37,7 +37,10 @@ __global__ void k_make_synthesis(int n_fft, int win, int bins, int ldk, int peri
         const double ck = (k == 0 || 2 * k == n_fft) ? 1.0 : 2.0;       // one-sided spectrum: interior bins count twice
         v = hann_any(n, win, periodic) * ck / n_fft * ((c & 1) ? -sin(ang) : cos(ang));
     }
-    split16<1>((float)v, shi[i], slo[i]);
+    // fp16 hi/lo of the forward operand: stored x n_fft (values up to 2 instead of 1.7e-3), so that the `lo` halves stay in
+    // fp16's normal range (unscaled they are ~1e-6, subnormal: the split would carry ~15 bits, not 22); the overlap-add
+    // multiplies by 1 / n_fft.  The transposed bf16 copy of the backward keeps the true values (bf16 has the fp32 exponent).
+    split16<1>((float)(v * n_fft), shi[i], slo[i]);
     if (c < 2 * bins) split16<0>((float)v, thi[(size_t)c * win + n], tlo[(size_t)c * win + n]);
 }
 
@@ -97,6 +100,7 @@ __global__ void k_loss_overlap_add(const float* __restrict__ frames /*[rows][win
         const int nidx = pos - t * hop;
         if (nidx >= 0 && nidx < win) { acc += frames[((size_t)b * T + t) * win + nidx]; wss += wsq[nidx]; }
     }
+    acc *= 0.5f / (float)half;                     // the synthesis operand is stored x n_fft (k_make_synthesis); half = n_fft / 2
     out[i] = wss > 1e-11f ? acc / wss : acc;
 }
 

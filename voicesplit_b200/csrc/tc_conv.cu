@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi,
         for (int i = 0; i < 8; ++i) {
             const int chunk = i * 256 + tid;
             const int px = chunk >> 3, part = chunk & 7;
+            if (F8C && pl == 1 && part >= 4) continue;      // c8 rows: only the l8 half (bytes 0..63) is read here
             if (p0 + px < nplane) {
                 const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + px * 144 + part * 16);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)chunk * 16) : "memory");

@@ -141,6 +141,11 @@ class MaskEngine:
             _cabi.check(self.lib.vs_forward_host_submit(self.handle, slot, _ptr(x_host), _ptr(emb_host), _ptr(mask_host),
                                                         _ptr(masked_host), B, T, self._prec(precision)), "vs_forward_host_submit")
 
+    def host_reserve(self, B, T, precision="fp16x3"):
+        """Allocate the device staging of the host entry points for batches up to (B, T) now, so no request allocates."""
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.vs_forward_host_reserve(self.handle, B, T, self._prec(precision)), "vs_forward_host_reserve")
+
     def host_wait(self, slot):
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.vs_forward_host_wait(self.handle, slot), "vs_forward_host_wait")
