@@ -39,8 +39,11 @@ namespace vs {
 using namespace ptx;
 
 constexpr int kWStages = 5;             // weight tiles (16 KB each) in flight
-constexpr int kEpiWarps = 16;           // epilogue warps (4 per TMEM lane quadrant)
-constexpr int kConvThreads = 64 + 32 * kEpiWarps;
+// Epilogue warps: 4 per TMEM lane quadrant for the flat tiles (N = 256: 8 chunks of 32 columns, two per warp).  The 2-D tiles of
+// cnn2 (N = 224: 7 chunks) have less than half the MMA work per tile (7 single-tap steps), so the epilogue sets their pace:
+// they run 7 warps per quadrant, one chunk each (960 threads, <= 64 registers).
+constexpr int kEpiWarpsFlat = 16, kEpiWarps2D = 28;
+constexpr int conv_threads(int ew) { return 64 + 32 * ew; }
 constexpr int kWTileBytes = 128 * 128;  // 128 rows x 64 bf16
 
 struct ConvTcArgs {
@@ -65,15 +68,15 @@ struct ConvTcArgs {
     float* out32;   // OUT32 kernels (training): fp32 plane [B][Q][64] instead of the 16-bit planes
 };
 
-template <int ACT>
+template <int ACT, bool LEAN = false>
 __device__ __forceinline__ float act_fast(float x) {
     if (ACT == 2) return x;   // pass-through: raw conv output (training forward before BatchNorm, data gradients)
     if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
-    return mish_f(x);
+    return LEAN ? mish_lean(x) : mish_f(x);
 }
 
-template <int ACT, int ELT, bool OUT32, bool F8C>
-__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
+template <int ACT, int ELT, bool OUT32, bool F8C, int EW>
+__global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
                                                     const __grid_constant__ CUtensorMap tm_w_hi,
                                                     const __grid_constant__ CUtensorMap tm_w_lo) {
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], (uint32_t)a.csz); }
         for (int i = 0; i < a.s_stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EW); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
             elt16* olo = (!OUT32 && want_lo) ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + (co & ~1) : nullptr;
             uint8_t* oc8 = (!OUT32 && F8C) ? reinterpret_cast<uint8_t*>(a.out_lo) + ((size_t)b * a.Q + q0) * 128 + (co & ~1) : nullptr;
             float* o32 = OUT32 ? a.out32 + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
-            for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (kEpiWarps / 4)) {
+            for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (EW / 4)) {
                 uint32_t r[32];
                 uint32_t nxt = 0;
                 tmem_ld_32x32(t_base + c0, r);
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                         const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
                         const float acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
                         const int fcur = a.tile2d ? f0 + ((c0 + 2 * mm + h) & 7) : f;
-                        y[i] = (fcur < a.F) ? act_fast<ACT>(fmaf(acc, sc, sh)) : 0.f;
+                        y[i] = (fcur < a.F) ? act_fast<ACT, F8C>(fmaf(acc, sc, sh)) : 0.f;
                         f += 2;
                         if (f >= a.Fp) f -= a.Fp;
                     }
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const ConvTcArgs a,
                         }
                     }
                 }
-                f = (f + 32 * (kEpiWarps / 4 - 1)) % a.Fp;   // skip the chunks the other warps take
+                f = (f + 32 * (EW / 4 - 1)) % a.Fp;   // skip the chunks the other warps take
             }
             tc_fence_before();
             __syncwarp();
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc = fmaf(wr[j][c], xv[p + j], acc);
-                    yv[c] = (f < F) ? act_fast<ACT>(fmaf(acc, sc[c], sh[c])) : 0.f;
+                    yv[c] = (f < F) ? act_fast<ACT, F8C>(fmaf(acc, sc[c], sh[c])) : 0.f;
                     if (F8C) split_f8c(yv[c], vh[c], rl[c]); else split16<ELT>(yv[c], vh[c], vl[c]);
                 }
                 const size_t o = ((size_t)row * Fp + f) * 64 + cg * 4;
@@ -795,24 +798,27 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)a.csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    const int ew = a.tile2d ? kEpiWarps2D : kEpiWarpsFlat;
+    cfg.blockDim = dim3(conv_threads(ew)); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = a.csz > 1 ? 1 : 0;
-#define VS_CONV_TC(A, E, O, F8)                                                                               \
-    do {                                                                                                      \
-        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-        int max_ctas = e->num_sms;                                                                            \
-        if (ce == cudaSuccess && a.csz > 1) {                                                                 \
-            int ncl = 0;                                                                                      \
-            cfg.gridDim = dim3((unsigned)(e->num_sms / a.csz * a.csz));                                       \
-            ce = cudaOccupancyMaxActiveClusters(&ncl, k_conv_tc<A, E, O, F8>, &cfg);                           \
+#define VS_CONV_TC_EW(A, E, O, F8, W)                                                                            \
+    do {                                                                                                         \
+        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+        int max_ctas = e->num_sms;                                                                               \
+        if (ce == cudaSuccess && a.csz > 1) {                                                                    \
+            int ncl = 0;                                                                                         \
+            cfg.gridDim = dim3((unsigned)(e->num_sms / a.csz * a.csz));                                          \
+            ce = cudaOccupancyMaxActiveClusters(&ncl, k_conv_tc<A, E, O, F8, W>, &cfg);                           \
             if (ce == cudaSuccess && ncl < 1) { set_error("conv clusters do not fit the device"); return VS_ERR_UNSUPPORTED; } \
-            max_ctas = ncl * a.csz < e->num_sms ? ncl * a.csz : e->num_sms / a.csz * a.csz;                    \
-        }                                                                                                     \
-        grid = a.total_tiles < max_ctas ? (a.total_tiles + a.csz - 1) / a.csz * a.csz : max_ctas;             \
-        a.n_iter = (a.total_tiles + grid - 1) / grid;                                                         \
-        cfg.gridDim = dim3((unsigned)grid);                                                                   \
-        if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_conv_tc<A, E, O, F8>, a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+            max_ctas = ncl * a.csz < e->num_sms ? ncl * a.csz : e->num_sms / a.csz * a.csz;                       \
+        }                                                                                                        \
+        grid = a.total_tiles < max_ctas ? (a.total_tiles + a.csz - 1) / a.csz * a.csz : max_ctas;                \
+        a.n_iter = (a.total_tiles + grid - 1) / grid;                                                            \
+        cfg.gridDim = dim3((unsigned)grid);                                                                      \
+        if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_conv_tc<A, E, O, F8, W>, a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
+#define VS_CONV_TC(A, E, O, F8)                                                                 \
+    do { if (a.tile2d) VS_CONV_TC_EW(A, E, O, F8, kEpiWarps2D); else VS_CONV_TC_EW(A, E, O, F8, kEpiWarpsFlat); } while (0)
     if (call.out32) {
         if (call.act != 2) { set_error("fp32-output conv is pass-through only"); return VS_ERR_INVALID; }
         if (elt) VS_CONV_TC(2, 1, true, false); else VS_CONV_TC(2, 0, true, false);
@@ -820,6 +826,7 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
         if (a.act == VS_ACT_RELU) VS_CONV_TC(VS_ACT_RELU, 1, false, true); else VS_CONV_TC(VS_ACT_MISH, 1, false, true);
     } else if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1, false, false); else VS_CONV_TC(VS_ACT_RELU, 0, false, false); }
     else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1, false, false); else VS_CONV_TC(VS_ACT_MISH, 0, false, false); }
+#undef VS_CONV_TC_EW
 #undef VS_CONV_TC
     if (ce == cudaSuccess) ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_error(std::string("k_conv_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
