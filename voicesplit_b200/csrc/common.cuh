@@ -28,21 +28,15 @@ __host__ __device__ inline int padded_freq(int F) { return ((F + 2 + 7) / 8) * 8
 // ---- activations -------------------------------------------------------------------------------
 // Mish: x * tanh(softplus(x)), softplus threshold 20 (reference utils/generic_utils.py:399).
 // tanh(log(1+e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = (e^2 + 2e) / (e^2 + 2e + 2); one exp, one divide.
+// Branch-free, 9 instructions (FMNMX, FMUL, EX2, FADD, FMUL, FADD, RCP, FMUL, FMUL), raw MUFU approximations (each ~1 ulp):
+// e is taken at min(x, 30), where n / (n + 2) is already exactly 1.0f (it is for x > 8.7), so large x return x without the
+// e^2 overflow; no range / denormal fix-up code, no divergent branch - the fused epilogues interleave many of these.
 __device__ __forceinline__ float mish_f(float x) {
-    if (x > 20.f) return x;  // tanh(x) == 1.0f in fp32 for x > 20 (and avoids e^2 overflow)
-    float e = __expf(x);
-    float n = e * (e + 2.f);
-    return x * __fdividef(n, n + 2.f);
-}
-// Leaner form for the FP16_F8C epilogues (whose operands carry ~2^-15 anyway): x t = x - 2x / (n + 2) with n + 2 = e (e + 2) + 2; seven instructions (FMUL, EX2, FADD,
-// FFMA, RCP, FMUL, FFMA) and no branch: for large x the denominator overflows to +inf, its reciprocal is 0 and the result is x
-// (the softplus threshold of the reference, exact in fp32 beyond x = 20); for very negative x it tends to x - x = 0 like
-// x e^x does.  Absolute error <= 1.3e-6 everywhere (the subtraction cancels two O(x) terms of ~1e-7 relative error each).
-__device__ __forceinline__ float mish_lean(float x) {
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(e, e + 2.f, 2.f)));
-    return fmaf(x * r, -2.f, x);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 30.f) * 1.4426950408889634f));
+    const float n = e * (e + 2.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.f));
+    return x * (n * r);
 }
 __device__ __forceinline__ float mish_precise(float x) {
     if (x > 20.f) return x;

@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace vs {
 using namespace ptx;
@@ -68,11 +69,11 @@ struct ConvTcArgs {
     float* out32;   // OUT32 kernels (training): fp32 plane [B][Q][64] instead of the 16-bit planes
 };
 
-template <int ACT, bool LEAN = false>
+template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
     if (ACT == 2) return x;   // pass-through: raw conv output (training forward before BatchNorm, data gradients)
     if (ACT == VS_ACT_RELU) return fmaxf(x, 0.f);
-    return LEAN ? mish_lean(x) : mish_f(x);
+    return mish_f(x);
 }
 
 template <int ACT, int ELT, bool OUT32, bool F8C, int EW>
@@ -274,92 +275,119 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
             }
         }
     } else {
-        // ===================== epilogue (warps 2..17) =====================
+        // ===================== epilogue (warps 2 ..) =====================
+        // The instruction stream of these warps is what bounds the light layers (cnn2: ~8.5 k issue cycles per tile and SM
+        // sub-partition against 6.3 k cycles of MMA), so it is kept branch-free and short: interior chunks (no row padding, no
+        // tile / plane edge: the common case) take a path without per-pixel bookkeeping, store addresses are one base pointer per
+        // chunk plus compile-time offsets, the activation is nine straight-line instructions (common.cuh: mish_f).
+        constexpr bool T2D = (EW == kEpiWarps2D);        // the launch pairs the 2-D tiles with this warp count
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
         const int cgrp = (warp - 2) >> 2;                // which 32-column chunks this warp takes
         const int co = quad * 16 + (lane >> 1), h = lane & 1;
         const float sc = a.scale[co], sh = a.shift[co];
-        const bool want_lo = !OUT32 && a.out_lo != nullptr;
+        const bool want_lo = !OUT32 && !F8C && a.out_lo != nullptr;
+        // 16-bit outputs: lanes L and L^2 hold channels co, co^1 of the same pixels; they swap every other value so that
+        // each lane stores a CHANNEL PAIR (4 bytes per plane) of every second pixel instead of 2 bytes of every pixel
+        const int codd = (lane >> 1) & 1;
+        const size_t row_px = T2D ? (size_t)a.Fp : 0;    // 2-D tiles: pixels between consecutive frames
         int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, aph = (it >> 1) & 1;
             const int b = tile / a.tiles_per_utt;
-            int q0 = (tile - b * a.tiles_per_utt) * useful;
-            int t0 = 0, f0 = 0;                          // 2-D tiles: first frame / bin; column p is frame t0 + p / 8, bin f0 + p % 8
-            if (a.tile2d) {
-                const int tin = tile - b * a.tiles_per_utt, tt = tin / a.n_ft;
-                t0 = tt * a.tr; f0 = (tin - tt * a.n_ft) * 8;
-                q0 = 0;
-            }
+            const int tin = tile - b * a.tiles_per_utt;
+            int q0 = 0, t0 = 0, f0 = 0;                  // flat: first pixel; 2-D: first frame / bin (column p = frame t0 + p / 8, bin f0 + p % 8)
+            if (T2D) { const int tt = tin / a.n_ft; t0 = tt * a.tr; f0 = (tin - tt * a.n_ft) * 8; }
+            else q0 = tin * useful;
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
-            int f = (q0 + h + cgrp * 32) % a.Fp;         // frequency index of this lane's first pixel (flat tiles)
-            // 16-bit outputs: lanes L and L^2 hold channels co, co^1 of the same pixels; they swap every other value so that
-            // each lane stores a CHANNEL PAIR (4 bytes per plane) of every second pixel instead of 2 bytes of every pixel
-            const int codd = (lane >> 1) & 1;
-            elt16* ohi = OUT32 ? nullptr : a.out_hi + ((size_t)b * a.Q + q0) * 64 + (co & ~1);
-            elt16* olo = (!OUT32 && want_lo) ? a.out_lo + ((size_t)b * a.Q + q0) * 64 + (co & ~1) : nullptr;
-            uint8_t* oc8 = (!OUT32 && F8C) ? reinterpret_cast<uint8_t*>(a.out_lo) + ((size_t)b * a.Q + q0) * 128 + (co & ~1) : nullptr;
-            float* o32 = OUT32 ? a.out32 + ((size_t)b * a.Q + q0) * 64 + co : nullptr;
+            const size_t plane0 = (size_t)b * a.Q;       // first pixel of the utterance's plane
             for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (EW / 4)) {
                 uint32_t r[32];
                 uint32_t nxt = 0;
                 tmem_ld_32x32(t_base + c0, r);
                 if (c0 + 32 < a.N)
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(nxt) : "r"(t_base + c0 + 32) : "memory");
+                // pixel of this lane's FIRST value of the chunk (column c0 + h) and whether the whole chunk is interior
+                size_t px0;
+                bool interior;
+                int f = 0;
+                if (T2D) {
+                    const int tr0 = t0 + (c0 >> 3);       // the chunk covers frames tr0 .. tr0 + 3, bins f0 .. f0 + 7
+                    px0 = (size_t)tr0 * a.Fp + f0 + h;
+                    interior = tr0 + 4 <= a.T && f0 + 8 <= a.F;
+                } else {
+                    px0 = (size_t)q0 + c0 + h;
+                    const int fc = (q0 + c0) % a.Fp;      // bin of the chunk's first column; rows are Fp pixels, bins >= F are padding
+                    f = fc + h; if (f >= a.Fp) f -= a.Fp;
+                    interior = fc + 33 <= a.F && c0 + 32 <= useful && q0 + c0 + 32 <= a.Q;
+                }
+                elt16* ohi = OUT32 ? nullptr : a.out_hi + (plane0 + px0) * 64 + (co & ~1);
+                elt16* olo = want_lo ? a.out_lo + (plane0 + px0) * 64 + (co & ~1) : nullptr;
+                uint8_t* oc8 = (!OUT32 && F8C) ? reinterpret_cast<uint8_t*>(a.out_lo) + (plane0 + px0) * 128 + (co & ~1) : nullptr;
+                float* o32 = OUT32 ? a.out32 + (plane0 + px0) * 64 + co : nullptr;
                 tmem_ld_wait();
+                auto body = [&](auto fast_tag) {
+                    constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
-                for (int m = 0; m < 16; m += 2) {
-                    float y[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        // even lane (h=0, lower tap) owns pixel c0+2(m+i), odd lane (upper tap) pixel c0+2(m+i)+1
-                        const int mm = m + i;
-                        const float mine_odd = __uint_as_float(r[2 * mm + 1]);
-                        const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
-                        const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
-                        const float acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
-                        const int fcur = a.tile2d ? f0 + ((c0 + 2 * mm + h) & 7) : f;
-                        y[i] = (fcur < a.F) ? act_fast<ACT, F8C>(fmaf(acc, sc, sh)) : 0.f;
-                        f += 2;
-                        if (f >= a.Fp) f -= a.Fp;
-                    }
-                    if (OUT32) {
+                    for (int m = 0; m < 16; m += 2) {
+                        float y[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
-                            int p = c0 + 2 * (m + i) + h;
-                            bool ok = p < useful && q0 + p < a.Q;
-                            if (a.tile2d) { ok = p < a.N && t0 + (p >> 3) < a.T; p = (t0 + (p >> 3)) * a.Fp + f0 + (p & 7); }
-                            if (ok) o32[(size_t)p * 64] = y[i];
+                            // even lane (h=0, lower tap) owns pixel c0+2(m+i), odd lane (upper tap) pixel c0+2(m+i)+1
+                            const int mm = m + i;
+                            const float mine_odd = __uint_as_float(r[2 * mm + 1]);
+                            const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
+                            const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
+                            const float acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
+                            y[i] = act_fast<ACT>(fmaf(acc, sc, sh));
+                            if (!FAST) {     // padding bins hold zeros (select, not a branch)
+                                const int fcur = T2D ? f0 + 2 * (mm & 3) + h : f;
+                                y[i] *= fcur < a.F ? 1.f : 0.f;
+                                f += 2;
+                                if (f >= a.Fp) f -= a.Fp;
+                            }
                         }
-                    } else {
-                        // channel-even lane keeps the first pixel, channel-odd lane the second; each receives the partner channel
-                        const float recv = __shfl_xor_sync(0xffffffffu, codd ? y[0] : y[1], 2);
-                        const float v0 = codd ? recv : y[0], v1 = codd ? y[1] : recv;      // channels (co & ~1), (co | 1)
-                        int p = c0 + 2 * (m + codd) + h;
-                        bool ok = p < useful && q0 + p < a.Q;
-                        if (a.tile2d) { ok = p < a.N && t0 + (p >> 3) < a.T; p = (t0 + (p >> 3)) * a.Fp + f0 + (p & 7); }
-                        if (ok) {
-                            if (F8C) {
-                                elt16 h0, h1;
-                                float l0, l1;
-                                split_f8c(v0, h0, l0);
-                                split_f8c(v1, h1, l1);
-                                *reinterpret_cast<uint32_t*>(ohi + (size_t)p * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                *reinterpret_cast<unsigned short*>(oc8 + (size_t)p * 128) = e4m3x2(kF8cLoScale * l0, kF8cLoScale * l1);
-                                *reinterpret_cast<unsigned short*>(oc8 + (size_t)p * 128 + 64) = e4m3x2(kF8cHiScale * v0, kF8cHiScale * v1);
-                            } else {
-                                elt16 h0, l0, h1, l1;
-                                split16<ELT>(v0, h0, l0);
-                                split16<ELT>(v1, h1, l1);
-                                *reinterpret_cast<uint32_t*>(ohi + (size_t)p * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                if (want_lo) *reinterpret_cast<uint32_t*>(olo + (size_t)p * 64) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                        // pixel offset (from px0) of value mm: flat 2 mm; 2-D (mm / 4) frames + 2 (mm % 4) bins - compile-time but for Fp
+                        auto off = [&](int mm) { return T2D ? (size_t)(mm >> 2) * row_px + 2 * (mm & 3) : (size_t)(2 * mm); };
+                        auto valid = [&](int mm) {
+                            if (FAST) return true;
+                            if (T2D) return t0 + ((c0 + 2 * mm) >> 3) < a.T;                 // bins: every tile covers 8 in-plane bins
+                            const int p = c0 + 2 * mm + h;
+                            return p < useful && q0 + p < a.Q;
+                        };
+                        if (OUT32) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                if (valid(m + i)) o32[off(m + i) * 64] = y[i];
+                        } else {
+                            // channel-even lane keeps the first pixel, channel-odd lane the second; each receives the partner channel
+                            const float recv = __shfl_xor_sync(0xffffffffu, codd ? y[0] : y[1], 2);
+                            const float v0 = codd ? recv : y[0], v1 = codd ? y[1] : recv;      // channels (co & ~1), (co | 1)
+                            // the kept pixel is value m (channel-even lanes) or m + 1 (channel-odd lanes): select between two offsets
+                            const size_t o = codd ? off(m + 1) : off(m);
+                            const bool ok = codd ? valid(m + 1) : valid(m);
+                            if (ok) {
+                                if (F8C) {
+                                    elt16 h0, h1;
+                                    float l0, l1;
+                                    split_f8c(v0, h0, l0);
+                                    split_f8c(v1, h1, l1);
+                                    *reinterpret_cast<uint32_t*>(ohi + o * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                    *reinterpret_cast<unsigned short*>(oc8 + o * 128) = e4m3x2(kF8cLoScale * l0, kF8cLoScale * l1);
+                                    *reinterpret_cast<unsigned short*>(oc8 + o * 128 + 64) = e4m3x2(kF8cHiScale * v0, kF8cHiScale * v1);
+                                } else {
+                                    elt16 h0, l0, h1, l1;
+                                    split16<ELT>(v0, h0, l0);
+                                    split16<ELT>(v1, h1, l1);
+                                    *reinterpret_cast<uint32_t*>(ohi + o * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                    if (want_lo) *reinterpret_cast<uint32_t*>(olo + o * 64) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                                }
                             }
                         }
                     }
-                }
-                f = (f + 32 * (EW / 4 - 1)) % a.Fp;   // skip the chunks the other warps take
+                };
+                if (interior) body(std::true_type{}); else body(std::false_type{});
             }
             tc_fence_before();
             __syncwarp();
@@ -414,7 +442,7 @@ __global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc = fmaf(wr[j][c], xv[p + j], acc);
-                    yv[c] = (f < F) ? act_fast<ACT, F8C>(fmaf(acc, sc[c], sh[c])) : 0.f;
+                    yv[c] = act_fast<ACT>(fmaf(acc, sc[c], sh[c])) * (f < F ? 1.f : 0.f);
                     if (F8C) split_f8c(yv[c], vh[c], rl[c]); else split16<ELT>(yv[c], vh[c], vl[c]);
                 }
                 const size_t o = ((size_t)row * Fp + f) * 64 + cg * 4;
