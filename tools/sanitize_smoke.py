@@ -13,7 +13,7 @@ eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items(
 x, emb = synth.make_inputs(3, 37, dims, 12)
 xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
 ref = eng.forward(xt, et, precision="fp32")
-for p in ("fp16x3", "bf16x3", "fp16", "bf16"):
+for p in ("fp16x3", "fp16_f8c", "bf16x3", "fp16", "bf16"):
     out = eng.forward(xt, et, precision=p, want_masked=True)[0]
     print(p, float((out - ref).abs().max()))
 m = VoiceSplit(config.AttrDict(synth.make_config_dict(dims)))
@@ -22,8 +22,9 @@ m = m.cuda().train()
 for tc in (True, False):
     m.train_tensor_cores = tc
     m.zero_grad()
-    m(xt, et).sum().backward()
-    print("train tc", tc, float(m.fc2.weight.grad.abs().max()))
+    xg = xt.clone().requires_grad_(True)
+    m(xg, et).sum().backward()
+    print("train tc", tc, float(m.fc2.weight.grad.abs().max()), "d/dx", float(xg.grad.abs().max()))
 d601 = synth.make_dims(601, 8, 16, 24)
 e2 = MaskEngine(activation="relu", **d601)
 e2.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in synth.make_state_dict(d601, 1, "default").items() if "num_batches" not in k})

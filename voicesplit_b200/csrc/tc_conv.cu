@@ -61,6 +61,8 @@ struct ConvTcArgs {
     // (tr + kh - 1) x 8 block around it, loaded ONCE per plane with a 4-D TMA box and shared by all kh taps: tap dt is the window
     // starting dt * 8 rows (= dt swizzle atoms) into the strip.  Flat tiles would fetch a fresh strip per tap (7x the bytes).
     int tile2d, tr, n_ft, T;
+    int tr_out, t_halo;   // 2-D tiles: output frames per tile (tr - 1: the upper tap of a pair lands one frame up), (kh - 1) / 2
+    int l2_prefetch;      // flat tiles: prefetch the next tile's strips into L2 (VOICESPLIT_CONV_L2PREFETCH=1; off by default: measured no gain)
     int act;
     const float* scale;
     const float* shift;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
     if (a.csz > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts onto them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int useful = a.tile2d ? a.N : a.N - 1;     // flat tiles lose one pixel to the tap-pair shift
+    const int useful = a.tile2d ? 8 * a.tr_out : a.N - 1;   // the tap-pair shift costs one pixel (flat) / one frame (2-D)
     // 3-pass modes: per tap row both strips (hi, lo) are resident; each weight tile is fetched once:
     // W_hi[j] multiplies S_hi and S_lo, W_lo[j] multiplies S_hi  (hi*hi + lo*hi + hi*lo).
     const int n_strip_loads = a.passes == 3 ? 2 : 1;
@@ -142,11 +144,29 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                         if (elect_one()) {
                             mbar_arrive_expect_tx(&s_full[ss], (uint32_t)strip_bytes);
                             tma_load_4d(s_ring + (size_t)ss * strip_bytes, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[ss], 0, ft * 8,
-                                        tt * a.tr - a.n_dt / 2, b);
+                                        tt * a.tr_out - a.t_halo, b);
                         }
                         __syncwarp();
                         if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
                     }
+                }
+                // Flat tiles: only two tap rows of strips fit next to the weight ring, so a strip is requested ~2.5 MMA steps before
+                // it is needed - enough for an L2 hit, not for a DRAM miss (the activation planes are the only DRAM-sourced
+                // operand).  Pull the strips of this CTA's NEXT tile into L2 now, a whole tile (~15 us) ahead.
+                if (!a.tile2d && a.l2_prefetch) {
+                    const int ntile = tile + (int)gridDim.x;
+                    if (ntile < a.total_tiles && elect_one()) {
+                        const int nb = ntile / a.tiles_per_utt;
+                        const int nq0 = (ntile - nb * a.tiles_per_utt) * useful;
+                        for (int dt = 0; dt < a.n_dt; ++dt) {
+                            const int qs = nq0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
+                            for (int i = 0; i < a.n_boxes; ++i) {
+                                tma_prefetch_l2_3d(&tm_in_hi, 0, qs + i * a.box_rows, nb);
+                                if (n_strip_loads == 2) tma_prefetch_l2_3d(&tm_in_lo, 0, qs + i * a.box_rows, nb);
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
                 for (int dt = 0; dt < a.n_dt; ++dt) {
                     const int qs = q0 - a.halo + (dt - a.n_dt / 2) * a.dt_stride;
@@ -197,6 +217,8 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
         {
             const uint32_t idesc = make_idesc_bf16(128, a.N, ELT);
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
+            const uint64_t w_desc0 = make_smem_desc(smem_u32(w_ring), 16, 1024, 2);     // slot 0 of the weight ring / strip ring
+            const uint64_t s_desc0 = make_smem_desc(smem_u32(s_ring), 16, 1024, 2);
             int ws = 0, wph = 0, ss = 0, sph = 0, it = 0;
             for (int itn = 0; itn < a.n_iter; ++itn) {
                 if (blockIdx.x + itn * gridDim.x >= a.total_tiles) {
@@ -215,54 +237,68 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)(buf * a.N);
                 uint32_t accumulate = 0;
-                uint32_t s_addr[2] = {0, 0};
+                // UMMA descriptors are built ONCE (ring base) and advanced by integer adds on the 14-bit (address >> 4) field:
+                // the issuing warp executes ~10 dependent-latency cycles per instruction, so every instruction between two MMA
+                // batches is tensor-pipe idle time (ncu source view: ~140 instructions per 8 MMAs before this, pipe 57-75 % active)
+                uint64_t s_desc[2] = {0, 0};
                 int s_stage[2] = {0, 0};
                 for (int dt = 0; dt < a.n_dt; ++dt) {
                     // strips of this tap row: hi in stage ss (, lo in the next stage); 2-D tiles: one strip pair for all taps,
-                    // tap dt reads the window dt * 8 rows further down
+                    // tap pair s reads the window 2 s frames (16 rows) further down
                     if (!a.tile2d || dt == 0) {
                         for (int sp = 0; sp < n_strip_loads; ++sp) {
                             mbar_wait(&s_full[ss], sph);
-                            s_addr[sp] = smem_u32(s_ring + (size_t)ss * strip_bytes);
+                            s_desc[sp] = s_desc0 + (uint64_t)((uint32_t)ss * (uint32_t)(strip_bytes >> 4));
                             s_stage[sp] = ss;
                             if (++ss == a.s_stages) { ss = 0; sph ^= 1; }
                         }
                     } else {
-                        for (int sp = 0; sp < n_strip_loads; ++sp) s_addr[sp] += 8 * 128;
+                        for (int sp = 0; sp < n_strip_loads; ++sp) s_desc[sp] += (16 * 128) >> 4;   // next tap pair: 2 frames = 16 rows down
                     }
-                    tc_fence_after();
                     for (int j = 0; j < a.n_j; ++j) {
-                        for (int wp = 0; wp < n_strip_loads; ++wp) {   // wp 0: W_hi x (S_hi, S_lo); wp 1: W_lo x S_hi
+                        // the weight tiles of this step (W_hi, then W_lo / the e4m3 correction tile) sit in consecutive ring slots:
+                        // wait for all of them, then ONE elected issue block per step
+                        int wsl[2];
+                        for (int wp = 0; wp < n_strip_loads; ++wp) {
                             mbar_wait(&w_full[ws], wph);
-                            tc_fence_after();
-                            const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWTileBytes);
-                            // descriptors of K slice k = descriptor of slice 0 + 2k in the (address >> 4) field
-                            const uint64_t a_desc = make_smem_desc(w_addr, 16, 1024, 2);
-                            if (elect_one()) {
-                                if (F8C) {
-                                    // wp 0: W_hi x S_hi as four kind::f16 MMAs (K = 16); wp 1: the e4m3 correction tile x the c8 strip as
-                                    // four kind::f8f6f4 MMAs (K = 32 bytes each): x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
-                                    const uint64_t b_desc = make_smem_desc(s_addr[wp] + (uint32_t)(2 * j) * 128, 16, 1024, 2);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (wp == 0) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k == 0 ? accumulate : 1u);
-                                        else umma_f8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1);
-                                    }
-                                } else {
-                                    const int n_sp = (wp == 0) ? n_strip_loads : 1;
-                                    for (int sp = 0; sp < n_sp; ++sp) {
-                                        const uint64_t b_desc = make_smem_desc(s_addr[sp] + (uint32_t)(2 * j) * 128, 16, 1024, 2);
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k)
-                                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k == 0 && sp == 0) ? accumulate : 1u);
-                                    }
-                                }
-                                if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
-                            }
-                            __syncwarp();
-                            accumulate = 1;
+                            wsl[wp] = ws;
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t b0 = s_desc[0] + (uint64_t)(16 * j);      // window start 2 j pixel rows further: 2 j * 128 B >> 4
+                            const uint64_t a0 = w_desc0 + (uint64_t)(wsl[0] * (kWTileBytes >> 4));
+                            if (F8C) {
+                                // W_hi x S_hi as four kind::f16 MMAs (K = 16), then the e4m3 correction tile x the c8 strip as four
+                                // kind::f8f6f4 MMAs (K = 32 bytes each): x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
+                                const uint64_t b1 = s_desc[1] + (uint64_t)(16 * j);
+                                const uint64_t a1 = w_desc0 + (uint64_t)(wsl[1] * (kWTileBytes >> 4));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                                if (a.csz > 1) umma_commit_mc(&w_empty[wsl[0]], cmask); else umma_commit(&w_empty[wsl[0]]);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_f8(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc8, 1);
+                                if (a.csz > 1) umma_commit_mc(&w_empty[wsl[1]], cmask); else umma_commit(&w_empty[wsl[1]]);
+                            } else {
+                                // W_hi x (S_hi, S_lo), then W_lo x S_hi  (hi*hi + lo*hi + hi*lo); single-pass modes: W_hi x S_hi only
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                                if (n_strip_loads == 2) {
+                                    const uint64_t b1 = s_desc[1] + (uint64_t)(16 * j);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);
+                                }
+                                if (a.csz > 1) umma_commit_mc(&w_empty[wsl[0]], cmask); else umma_commit(&w_empty[wsl[0]]);
+                                if (n_strip_loads == 2) {
+                                    const uint64_t a1 = w_desc0 + (uint64_t)(wsl[1] * (kWTileBytes >> 4));
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1);
+                                    if (a.csz > 1) umma_commit_mc(&w_empty[wsl[1]], cmask); else umma_commit(&w_empty[wsl[1]]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        accumulate = 1;
                     }
                     if (!a.tile2d || dt == a.n_dt - 1) {
                         if (elect_one())
@@ -296,7 +332,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
             const int b = tile / a.tiles_per_utt;
             const int tin = tile - b * a.tiles_per_utt;
             int q0 = 0, t0 = 0, f0 = 0;                  // flat: first pixel; 2-D: first frame / bin (column p = frame t0 + p / 8, bin f0 + p % 8)
-            if (T2D) { const int tt = tin / a.n_ft; t0 = tt * a.tr; f0 = (tin - tt * a.n_ft) * 8; }
+            if (T2D) { const int tt = tin / a.n_ft; t0 = tt * a.tr_out; f0 = (tin - tt * a.n_ft) * 8; }
             else q0 = tin * useful;
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
@@ -304,10 +340,16 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
             const size_t plane0 = (size_t)b * a.Q;       // first pixel of the utterance's plane
             for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (EW / 4)) {
                 uint32_t r[32];
-                uint32_t nxt = 0;
+                uint32_t nxt = 0;                         // flat: column c0 + 32 (the upper tap of the chunk's last pixel)
+                uint32_t rx[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // 2-D: columns c0 + 32 .. c0 + 39 (the upper tap sits one frame = 8 columns on)
                 tmem_ld_32x32(t_base + c0, r);
-                if (c0 + 32 < a.N)
+                if (T2D) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(rx[0]), "=r"(rx[1]), "=r"(rx[2]), "=r"(rx[3]), "=r"(rx[4]), "=r"(rx[5]), "=r"(rx[6]), "=r"(rx[7])
+                                 : "r"(t_base + c0 + 32) : "memory");
+                } else if (c0 + 32 < a.N) {
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(nxt) : "r"(t_base + c0 + 32) : "memory");
+                }
                 // pixel of this lane's FIRST value of the chunk (column c0 + h) and whether the whole chunk is interior
                 size_t px0;
                 bool interior;
@@ -315,7 +357,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                 if (T2D) {
                     const int tr0 = t0 + (c0 >> 3);       // the chunk covers frames tr0 .. tr0 + 3, bins f0 .. f0 + 7
                     px0 = (size_t)tr0 * a.Fp + f0 + h;
-                    interior = tr0 + 4 <= a.T && f0 + 8 <= a.F;
+                    interior = tr0 + 4 <= a.T && f0 + 8 <= a.F && c0 + 32 <= useful;
                 } else {
                     px0 = (size_t)q0 + c0 + h;
                     const int fc = (q0 + c0) % a.Fp;      // bin of the chunk's first column; rows are Fp pixels, bins >= F are padding
@@ -336,10 +378,19 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                         for (int i = 0; i < 2; ++i) {
                             // even lane (h=0, lower tap) owns pixel c0+2(m+i), odd lane (upper tap) pixel c0+2(m+i)+1
                             const int mm = m + i;
-                            const float mine_odd = __uint_as_float(r[2 * mm + 1]);
-                            const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
-                            const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
-                            const float acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
+                            float acc;
+                            if (T2D) {
+                                // out[n] = D[2co][n] + D[2co+1][n + 8]: the even lane (row 2co) needs its neighbour's column 2mm + 8,
+                                // the odd lane (row 2co+1, pixel 2mm + 1) needs the even lane's column 2mm + 1 and its own 2mm + 9
+                                auto col = [&](int c) { return __uint_as_float(c < 32 ? r[c & 31] : rx[(c - 32) & 7]); };
+                                const float recv = __shfl_xor_sync(0xffffffffu, h ? col(2 * mm + 8) : col(2 * mm + 1), 1);
+                                acc = h == 0 ? col(2 * mm) + recv : recv + col(2 * mm + 9);
+                            } else {
+                                const float mine_odd = __uint_as_float(r[2 * mm + 1]);
+                                const float other_odd = __shfl_xor_sync(0xffffffffu, mine_odd, 1);
+                                const float up_next = __uint_as_float(mm < 15 ? r[(2 * mm + 2) & 31] : nxt);
+                                acc = h == 0 ? __uint_as_float(r[2 * mm]) + other_odd : other_odd + up_next;
+                            }
                             y[i] = act_fast<ACT>(fmaf(acc, sc, sh));
                             if (!FAST) {     // padding bins hold zeros (select, not a branch)
                                 const int fcur = T2D ? f0 + 2 * (mm & 3) + h : f;
@@ -352,7 +403,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                         auto off = [&](int mm) { return T2D ? (size_t)(mm >> 2) * row_px + 2 * (mm & 3) : (size_t)(2 * mm); };
                         auto valid = [&](int mm) {
                             if (FAST) return true;
-                            if (T2D) return t0 + ((c0 + 2 * mm) >> 3) < a.T;                 // bins: every tile covers 8 in-plane bins
+                            if (T2D) return c0 + 2 * mm < useful && t0 + ((c0 + 2 * mm) >> 3) < a.T;   // bins: every tile covers 8 in-plane bins
                             const int p = c0 + 2 * mm + h;
                             return p < useful && q0 + p < a.Q;
                         };
@@ -592,31 +643,39 @@ __device__ __forceinline__ float pow2_scale(unsigned int maxbits) {
     return exp2f((float)(9 - ex));
 }
 // weights [tap][ci][co] fp32 -> tap-pair tiles [step][row = 2co+h][ci], scaled by s, as bf16 and fp16 hi / lo
+// Tap carried by weight-tile row 2co+h of step `step` (-1: padding slot).  Default: the two taps of a row pair are neighbours
+// along F (df = 2j, 2j+1 of filter row dt).  pair_t (the kw = 1 layer on 2-D tiles): neighbours along T (dt = 2 step, 2 step + 1).
+__device__ __forceinline__ int conv_tile_tap(int step, int h, int kh, int kw, int n_j, int pair_t) {
+    if (pair_t) { const int dt = 2 * step + h; return dt < kh ? dt * kw : -1; }
+    const int dt = step / n_j, df = 2 * (step % n_j) + h;
+    return df < kw ? dt * kw + df : -1;
+}
+__host__ __device__ inline int conv_tile_steps(int kh, int kw, int pair_t) { return pair_t ? (kh + 1) / 2 : kh * ((kw + 1) / 2); }
 __global__ void k_pack_conv_tc(const float* __restrict__ w32, const unsigned int* __restrict__ maxbits, elt16* __restrict__ bhi,
-                               elt16* __restrict__ blo, elt16* __restrict__ hhi, elt16* __restrict__ hlo, int kh, int kw, int n_j) {
+                               elt16* __restrict__ blo, elt16* __restrict__ hhi, elt16* __restrict__ hlo, int kh, int kw, int n_j, int pair_t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = kh * n_j * 128 * 64;
+    int n = conv_tile_steps(kh, kw, pair_t) * 128 * 64;
     if (i >= n) return;
     const float s = pow2_scale(*maxbits);
     int ci = i & 63, row = (i >> 6) & 127, step = i >> 13;
-    int dt = step / n_j, j = step % n_j;
-    int co = row >> 1, h = row & 1, df = 2 * j + h;
-    float v = (df < kw) ? s * w32[((size_t)(dt * kw + df) * 64 + ci) * 64 + co] : 0.f;
+    int co = row >> 1, h = row & 1;
+    const int tap = conv_tile_tap(step, h, kh, kw, n_j, pair_t);
+    float v = tap >= 0 ? s * w32[((size_t)tap * 64 + ci) * 64 + co] : 0.f;
     split16<0>(v, bhi[i], blo[i]);
     split16<1>(v, hhi[i], hlo[i]);
 }
 // VS_PREC_FP16_F8C correction tiles, same [step][row = 2co+h] order, 128 bytes per row:
 // [ e4m3(2^-8 * w_hi)[ci] x 64 | e4m3(2^2 * w_lo)[ci] x 64 ]  with  w = s * weight = w_hi (fp16) + w_lo
 __global__ void k_pack_conv_f8c(const float* __restrict__ w32, const unsigned int* __restrict__ maxbits, uint8_t* __restrict__ w8, int kh, int kw,
-                                int n_j) {
+                                int n_j, int pair_t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = kh * n_j * 128 * 64;
+    int n = conv_tile_steps(kh, kw, pair_t) * 128 * 64;
     if (i >= n) return;
     const float s = pow2_scale(*maxbits);
     int ci = i & 63, row = (i >> 6) & 127, step = i >> 13;
-    int dt = step / n_j, j = step % n_j;
-    int co = row >> 1, h = row & 1, df = 2 * j + h;
-    float v = (df < kw) ? s * w32[((size_t)(dt * kw + df) * 64 + ci) * 64 + co] : 0.f;
+    int co = row >> 1, h = row & 1;
+    const int tap = conv_tile_tap(step, h, kh, kw, n_j, pair_t);
+    float v = tap >= 0 ? s * w32[((size_t)tap * 64 + ci) * 64 + co] : 0.f;
     elt16 hi;
     float lo;
     split_f8c(v, hi, lo);
@@ -647,15 +706,23 @@ struct TcState {
     int max_smem = 0;
     int cluster = 2;          // CTAs per cluster sharing the conv weight fetches (VOICESPLIT_CONV_CLUSTER = 1, 2, 4 or 8)
     int tile2d = 1;           // 2-D tiles for the kw = 1 layer (VOICESPLIT_CONV_TILE2D = 0 falls back to flat tiles)
+    int tile2d_dgrad = 1;     // the same for the data-gradient use of that layer (VOICESPLIT_CONV_TILE2D_DGRAD)
+    int l2_prefetch = 0;      // flat tiles: L2 prefetch of the next tile's strips (VOICESPLIT_CONV_L2PREFETCH = 1 enables; measured: no gain)
 };
 
 static int tile_n_for(const vs_engine*) { return 256; }
+// the kw = 1 layer (cnn2) runs on 2-D tiles with its taps paired along T
+static bool conv_pairs_rows(const TcState* s, const ConvGeom& g, bool dgrad = false) {
+    return g.kw == 1 && g.dil == 1 && (dgrad ? s->tile2d_dgrad : s->tile2d);
+}
 
 int tc_create(vs_engine* e) {
     TcState* s = new TcState();
     e->tc = s;
     cudaDeviceGetAttribute(&s->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
-    if (const char* c = getenv("VOICESPLIT_CONV_TILE2D")) s->tile2d = atoi(c) != 0;
+    if (const char* c = getenv("VOICESPLIT_CONV_TILE2D")) s->tile2d = s->tile2d_dgrad = atoi(c) != 0;
+    if (const char* c = getenv("VOICESPLIT_CONV_TILE2D_DGRAD")) s->tile2d_dgrad = atoi(c) != 0;
+    if (const char* c = getenv("VOICESPLIT_CONV_L2PREFETCH")) s->l2_prefetch = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_CLUSTER")) {
         const int v = atoi(c);
         if (v == 1 || v == 2 || v == 4 || v == 8) s->cluster = v;
@@ -696,14 +763,15 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
             VS_CUDA_TRY(cudaMalloc(&s->unscale[l], 64 * sizeof(float)));
         }
         const int nw = g.cout * g.cin * g.kh * g.kw;
+        const int pair_t = conv_pairs_rows(s, g) ? 1 : 0;      // cnn2 on 2-D tiles: tap pairs along T
         k_absmax<<<(nw + 255) / 256, 256, 0, st>>>(e->conv_w32[l], nw, s->wmax + l);
         k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_hi[0][l], s->w_lo[0][l],
-                                                                    s->w_hi[1][l], s->w_lo[1][l], g.kh, g.kw, n_j);
-        k_pack_conv_f8c<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_c8[l], g.kh, g.kw, n_j);
+                                                                    s->w_hi[1][l], s->w_lo[1][l], g.kh, g.kw, n_j, pair_t);
+        k_pack_conv_f8c<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_w32[l], s->wmax + l, s->w_c8[l], g.kh, g.kw, n_j, pair_t);
         k_scale_tc<<<1, 64, 0, st>>>(e->conv_scale[l], s->wmax + l, s->scale_tc[l], 64);
         // training: the same power-of-two scale serves the flipped/transposed data-gradient weights (same values)
         k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_wT32[l], s->wmax + l, s->wT_hi[0][l], s->wT_lo[0][l],
-                                                                    s->wT_hi[1][l], s->wT_lo[1][l], g.kh, g.kw, n_j);
+                                                                    s->wT_hi[1][l], s->wT_lo[1][l], g.kh, g.kw, n_j, conv_pairs_rows(s, g, true) ? 1 : 0);
         k_scale_tc<<<1, 64, 0, st>>>(e->ones64, s->wmax + l, s->unscale[l], 64);
     }
     VS_CUDA_TRY(cudaGetLastError());
@@ -720,6 +788,7 @@ struct ConvTcCall {            // what differs between the eval layers and the t
     float* out32;              // non-null: fp32 output plane
     int kid;
     bool f8c = false;          // w_lo = e4m3 correction tiles, in_lo / out_lo = c8 planes
+    bool dgrad = false;        // data-gradient use (flipped / transposed weights)
 };
 static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const elt16* in_lo, elt16* out_hi, elt16* out_lo, int B, int T,
                              int passes, int elt, const ConvTcCall& call, cudaStream_t st);
@@ -740,6 +809,7 @@ int tc_train_conv(vs_engine* e, int layer, bool dgrad, const elt16* in_hi, const
     TcState* s = (TcState*)e->tc;
     ConvTcCall call{dgrad ? s->wT_hi[elt][layer] : s->w_hi[elt][layer], dgrad ? s->wT_lo[elt][layer] : s->w_lo[elt][layer], s->unscale[layer],
                     shift, 2, out32, kid};
+    call.dgrad = dgrad;
     return launch_conv_tc_ex(e, layer, in_hi, in_lo, nullptr, nullptr, B, T, 3, elt, call, st);
 }
 
@@ -759,13 +829,20 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     a.f8c = call.f8c ? 1 : 0;
     if (call.f8c && (passes != 3 || !elt || call.out32 || !in_lo || !out_lo)) { set_error("fp16_f8c conv needs the fp16 hi + c8 plane pair"); return VS_ERR_INVALID; }
     a.T = T;
+    a.l2_prefetch = s->l2_prefetch;
     // kw = 1 (cnn2): 2-D tiles of tr frames x 8 bins whose (tr + kh - 1) x 8 input block is loaded once for all kh taps
-    a.tile2d = (g.kw == 1 && g.dil == 1 && s->tile2d) ? 1 : 0;
+    a.tile2d = conv_pairs_rows(s, g, call.dgrad) ? 1 : 0;
     if (a.tile2d) {
+        // tap pairs along T: row 2co+h of step s carries tap dt = 2s + h; both halves see the window that starts 2s frames into
+        // the strip, so the upper tap's products belong to the output one frame up: out[r] = D[2co][r] + D[2co+1][r + 1] (a shift
+        // of 8 accumulator columns).  4 steps instead of 7; a window of tr frames yields tr - 1 output frames.
         a.tr = 28;                                  // N = 224: two strip pairs of 34 x 8 rows + the weight ring fit shared memory
+        a.tr_out = a.tr - 1;
+        a.t_halo = g.kh / 2;
+        a.n_dt = (g.kh + 1) / 2; a.n_j = 1;
         a.N = 8 * a.tr;
         a.n_ft = Fp / 8;
-        a.tiles_per_utt = a.n_ft * ((T + a.tr - 1) / a.tr);
+        a.tiles_per_utt = a.n_ft * ((T + a.tr_out - 1) / a.tr_out);
         a.total_tiles = B * a.tiles_per_utt;
     }
     a.strip_rows = a.tile2d ? (a.tr + g.kh - 1) * 8 : a.N + 8;
