@@ -440,7 +440,6 @@ def train_config4(dev, dist, rank, world, want_batch, barrier, steps=3, warmup=2
     model = VoiceSplit(vconfig.AttrDict(synth.make_config_dict(dims)))
     model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_state_dict(dims, 0, "default").items()})
     model = model.to(dev).train()
-    model.enable_data_parallel(dist, sync_bn=False, overlap=True)
     eng = model.engine(dev)
     free, _total = torch.cuda.mem_get_info(dev)
     free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
@@ -451,20 +450,44 @@ def train_config4(dev, dist, rank, world, want_batch, barrier, steps=3, warmup=2
         if need <= free:
             break
         B //= 2
-    if dist is not None:
-        t = torch.tensor([B], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        B = int(t.item())
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    x, emb = synth.make_inputs(min(B, 32), T, dims, 7 + rank)
-    reps = (B + x.shape[0] - 1) // x.shape[0]
-    x = torch.from_numpy(np.tile(x, (reps, 1, 1))[:B]).to(dev)
-    emb = torch.from_numpy(np.tile(emb, (reps, 1))[:B]).to(dev)
-    x = (x + 0.01 * torch.rand_like(x)).clamp_(0, 1)             # utterances differ (tiling only bounds the host-side generation time)
-    target = torch.rand(B, T, F, device=dev) * x
-    phase = (torch.rand(B, T, F, device=dev) * 2 - 1) * np.pi
-    seq_len = torch.full((B, 1), 160 * (T - 1), device=dev, dtype=torch.int64)
     crit = SpecSiSNRLoss(eng, dict(n_fft=1200, hop_length=160, win_length=400), "q1")
+    # One LOCAL step (no collective in it: the data-parallel hooks are installed afterwards) proves that the batch fits on every rank;
+    # the ranks then agree, so a rank that ran out of memory cannot leave the others waiting in a gradient all-reduce.
+    while True:
+        if dist is not None:
+            t = torch.tensor([B], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            B = int(t.item())
+        ok, err = 1, ""
+        try:
+            x, emb = synth.make_inputs(min(B, 32), T, dims, 7 + rank)
+            reps = (B + x.shape[0] - 1) // x.shape[0]
+            x = torch.from_numpy(np.tile(x, (reps, 1, 1))[:B]).to(dev)
+            emb = torch.from_numpy(np.tile(emb, (reps, 1))[:B]).to(dev)
+            x = (x + 0.01 * torch.rand_like(x)).clamp_(0, 1)         # utterances differ (tiling only bounds the host-side generation time)
+            target = torch.rand(B, T, F, device=dev) * x
+            phase = (torch.rand(B, T, F, device=dev) * 2 - 1) * np.pi
+            seq_len = torch.full((B, 1), 160 * (T - 1), device=dev, dtype=torch.int64)
+            opt.zero_grad(set_to_none=True)
+            crit(model(x, emb) * x, target, phase, seq_len).backward()
+            opt.step()
+            torch.cuda.synchronize()
+        except (torch.OutOfMemoryError, RuntimeError) as ex:
+            ok, err = 0, repr(ex)[:200]
+        if dist is not None:
+            t = torch.tensor([ok], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        if ok:
+            break
+        x = emb = target = phase = None
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        if B <= 8:
+            raise RuntimeError(f"training step does not fit at {B} utterances per GPU: {err}")
+        B //= 2
+    model.enable_data_parallel(dist, sync_bn=False, overlap=True)
     ar_events = []
 
     def step(record=False):
