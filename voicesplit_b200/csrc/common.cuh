@@ -67,6 +67,25 @@ __device__ __forceinline__ void split16(float y, elt16& hi, elt16& lo) {
         lo = __half_as_ushort(__float2half_rn(y - __half2float(h)));
     }
 }
+// two activations (bounded below: Mish / ReLU outputs) -> packed hi pair and packed lo pair, one pack instruction each
+template <int ELT>
+__device__ __forceinline__ void split16_pair(float v0, float v1, uint32_t& hi2, uint32_t& lo2) {
+    if (ELT == 0) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        hi2 = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+        lo2 = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+        v0 = fminf(v0, 60000.f);
+        v1 = fminf(v1, 60000.f);
+        const __half2 h = __floats2half2_rn(v0, v1);
+        hi2 = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+        lo2 = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
 __device__ __forceinline__ void split16_rt(float y, int elt, elt16& hi, elt16& lo) {
     if (elt == 0) split16<0>(y, hi, lo); else split16<1>(y, hi, lo);
 }
@@ -90,6 +109,18 @@ __device__ __forceinline__ void split_f8c(float y, elt16& hi, float& lo) {
     const __half h = __float2half_rn(y);
     hi = __half_as_ushort(h);
     lo = y - __half2float(h);
+}
+// The same for the two channels a lane stores together, straight to the stored words: hi2 = packed fp16 pair (one F2FP), l8 / x8 =
+// the two e4m3 pairs of the c8 row.  Only the upper clamp: the values are activations (Mish >= -0.31, ReLU >= 0).
+__device__ __forceinline__ void split_f8c_pair(float v0, float v1, uint32_t& hi2, unsigned short& l8, unsigned short& x8) {
+    v0 = fminf(v0, 60000.f);
+    v1 = fminf(v1, 60000.f);
+    const __half2 h = __floats2half2_rn(v0, v1);
+    hi2 = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    l8 = e4m3x2(kF8cLoScale * (v0 - hf.x), kF8cLoScale * (v1 - hf.y));
+    const __half2 q = __hmul2(h, __float2half2_rn(kF8cHiScale));      // x8 = e4m3(2^-2 * hi): one HMUL2 + one conversion for the pair
+    x8 = (unsigned short)__nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&q), __NV_SATFINITE, __NV_E4M3);
 }
 __device__ __forceinline__ float join16(elt16 hi, elt16 lo, int elt) {
     return elt == 0 ? __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo))

@@ -368,6 +368,12 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                 elt16* olo = want_lo ? a.out_lo + (plane0 + px0) * 64 + (co & ~1) : nullptr;
                 uint8_t* oc8 = (!OUT32 && F8C) ? reinterpret_cast<uint8_t*>(a.out_lo) + (plane0 + px0) * 128 + (co & ~1) : nullptr;
                 float* o32 = OUT32 ? a.out32 + (plane0 + px0) * 64 + co : nullptr;
+                if (!OUT32) {        // channel-odd lanes keep the SECOND pixel of every pair (2 pixels on, same frame): fold it into the bases
+                    const size_t lane_px = codd ? 2 : 0;
+                    ohi += lane_px * 64;
+                    if (want_lo) olo += lane_px * 64;
+                    if (F8C) oc8 += lane_px * 128;
+                }
                 tmem_ld_wait();
                 auto body = [&](auto fast_tag) {
                     constexpr bool FAST = decltype(fast_tag)::value;
@@ -415,24 +421,22 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                             // channel-even lane keeps the first pixel, channel-odd lane the second; each receives the partner channel
                             const float recv = __shfl_xor_sync(0xffffffffu, codd ? y[0] : y[1], 2);
                             const float v0 = codd ? recv : y[0], v1 = codd ? y[1] : recv;      // channels (co & ~1), (co | 1)
-                            // the kept pixel is value m (channel-even lanes) or m + 1 (channel-odd lanes): select between two offsets
-                            const size_t o = codd ? off(m + 1) : off(m);
+                            // the kept pixel is value m (channel-even lanes) or m + 1 (channel-odd lanes: already in the lane's base pointers)
+                            const size_t o = off(m);
                             const bool ok = codd ? valid(m + 1) : valid(m);
                             if (ok) {
                                 if (F8C) {
-                                    elt16 h0, h1;
-                                    float l0, l1;
-                                    split_f8c(v0, h0, l0);
-                                    split_f8c(v1, h1, l1);
-                                    *reinterpret_cast<uint32_t*>(ohi + o * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                    *reinterpret_cast<unsigned short*>(oc8 + o * 128) = e4m3x2(kF8cLoScale * l0, kF8cLoScale * l1);
-                                    *reinterpret_cast<unsigned short*>(oc8 + o * 128 + 64) = e4m3x2(kF8cHiScale * v0, kF8cHiScale * v1);
+                                    uint32_t hi2;
+                                    unsigned short l8, x8;
+                                    split_f8c_pair(v0, v1, hi2, l8, x8);
+                                    *reinterpret_cast<uint32_t*>(ohi + o * 64) = hi2;
+                                    *reinterpret_cast<unsigned short*>(oc8 + o * 128) = l8;
+                                    *reinterpret_cast<unsigned short*>(oc8 + o * 128 + 64) = x8;
                                 } else {
-                                    elt16 h0, l0, h1, l1;
-                                    split16<ELT>(v0, h0, l0);
-                                    split16<ELT>(v1, h1, l1);
-                                    *reinterpret_cast<uint32_t*>(ohi + o * 64) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                    if (want_lo) *reinterpret_cast<uint32_t*>(olo + o * 64) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                                    uint32_t hi2, lo2;
+                                    split16_pair<ELT>(v0, v1, hi2, lo2);
+                                    *reinterpret_cast<uint32_t*>(ohi + o * 64) = hi2;
+                                    if (want_lo) *reinterpret_cast<uint32_t*>(olo + o * 64) = lo2;
                                 }
                             }
                         }
@@ -486,26 +490,30 @@ __global__ void __launch_bounds__(256, 3) k_front_tc(const float* __restrict__ x
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const int f = f0 + p;
-                __align__(8) elt16 vh[4], vl[4];
-                float yv[4], rl[4];
+                float yv[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc = fmaf(wr[j][c], xv[p + j], acc);
                     yv[c] = act_fast<ACT>(fmaf(acc, sc[c], sh[c])) * (f < F ? 1.f : 0.f);
-                    if (F8C) split_f8c(yv[c], vh[c], rl[c]); else split16<ELT>(yv[c], vh[c], vl[c]);
                 }
                 const size_t o = ((size_t)row * Fp + f) * 64 + cg * 4;
-                *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(vh);
                 if (F8C) {   // `lo` is the c8 plane: 128 bytes per pixel, [l8 x 64 | x8 x 64]
+                    uint32_t h01, h23;
+                    unsigned short l01, l23, x01, x23;
+                    split_f8c_pair(yv[0], yv[1], h01, l01, x01);
+                    split_f8c_pair(yv[2], yv[3], h23, l23, x23);
+                    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h01, h23);
                     uint8_t* c8 = reinterpret_cast<uint8_t*>(lo) + ((size_t)row * Fp + f) * 128 + cg * 4;
-                    *reinterpret_cast<uint32_t*>(c8) = (uint32_t)e4m3x2(kF8cLoScale * rl[0], kF8cLoScale * rl[1]) |
-                                                       ((uint32_t)e4m3x2(kF8cLoScale * rl[2], kF8cLoScale * rl[3]) << 16);
-                    *reinterpret_cast<uint32_t*>(c8 + 64) = (uint32_t)e4m3x2(kF8cHiScale * yv[0], kF8cHiScale * yv[1]) |
-                                                            ((uint32_t)e4m3x2(kF8cHiScale * yv[2], kF8cHiScale * yv[3]) << 16);
-                } else if (lo) {
-                    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(vl);
+                    *reinterpret_cast<uint32_t*>(c8) = (uint32_t)l01 | ((uint32_t)l23 << 16);
+                    *reinterpret_cast<uint32_t*>(c8 + 64) = (uint32_t)x01 | ((uint32_t)x23 << 16);
+                } else {
+                    uint32_t h01, h23, l01, l23;
+                    split16_pair<ELT>(yv[0], yv[1], h01, l01);
+                    split16_pair<ELT>(yv[2], yv[3], h23, l23);
+                    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h01, h23);
+                    if (lo) *reinterpret_cast<uint2*>(lo + o) = make_uint2(l01, l23);
                 }
             }
         }
@@ -592,6 +600,159 @@ __global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi,
             if (xlo) xlo[o] = yl;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cnn8 on tensor cores.  The channels-last plane IS a K-major A operand: D[128 pixels][16 (8 used)] = A[128 px][64 ch] * W8[16][64]^T,
+// so a tile is one TMA box of 128 pixel rows and 4 small MMAs per operand plane; the kernel then runs at the plane's HBM read rate
+// instead of the issue rate of 512 FMAs + 128 shared-memory weight loads per pixel.
+//   mode 0  one 16-bit pass              a_hi * w_hi
+//   mode 1  split operands, 3 passes     a_hi * w_hi + a_lo * w_hi + a_hi * w_lo
+//   mode 2  VS_PREC_FP16_F8C             a_hi * w_hi + a_hi * w_lo (both kind::f16: the weight tile is 2 KB, a second fp16 pass costs nothing
+//                                        here) + l8 * e4m3(2^-8 w_hi) over the 64-byte l8 half of the c8 row (x8 is not read: 192 B / pixel)
+// Warp 0: TMA producer (ring of pixel tiles), warp 1: MMA issuer (4 accumulators of 16 TMEM columns), warps 2..13: three epilogue
+// groups of 4 warps (thread = one pixel x 8 channels: BN + act, 16-bit hi / lo of the LSTM operand at column c * F + f).
+// ---------------------------------------------------------------------------------------------
+constexpr int kP8Groups = 3, kP8Acc = 4;
+constexpr int kP8Threads = 64 + 128 * kP8Groups;
+struct Point8Args {
+    int mode, stages, stage_bytes, n_tiles;
+    long long nplane;
+    int F, Fp, ldx;
+    const float *scale, *shift;      // per output channel; scale already divided by the power-of-two weight scale
+    float* x32;
+    elt16 *xhi, *xlo;
+};
+template <int ACT, int ELT>
+__global__ void __launch_bounds__(kP8Threads, 1) k_point8_mma(const Point8Args a, const __grid_constant__ CUtensorMap tm_hi,
+                                                               const __grid_constant__ CUtensorMap tm_lo,
+                                                               const __grid_constant__ CUtensorMap tm_w16,
+                                                               const __grid_constant__ CUtensorMap tm_w8) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_hi = smem;                 // [16 rows][128 B] 128B swizzle
+    uint8_t* w_lo = smem + 2048;
+    uint8_t* w_8 = smem + 4096;           // [16 rows][64 B] e4m3, 64B swizzle
+    uint8_t* ring = smem + 8192;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * a.stage_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + a.stages;
+    uint64_t* acc_full = a_empty + a.stages;
+    uint64_t* acc_empty = acc_full + kP8Acc;
+    uint64_t* w_full = acc_empty + kP8Acc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kP8Acc; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(w_full, 4096u + (a.mode == 2 ? 1024u : 0u));
+            tma_load_2d(w_hi, &tm_w16, w_full, 0, 0);
+            tma_load_2d(w_lo, &tm_w16, w_full, 0, 16);
+            if (a.mode == 2) tma_load_2d(w_8, &tm_w8, w_full, 0, 0);
+        }
+        __syncwarp();
+        int st = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            mbar_wait(&a_empty[st], ph ^ 1);
+            if (elect_one()) {
+                uint8_t* dst = ring + (size_t)st * a.stage_bytes;
+                mbar_arrive_expect_tx(&a_full[st], (uint32_t)a.stage_bytes);
+                tma_load_2d(dst, &tm_hi, &a_full[st], 0, tile * 128);
+                if (a.mode != 0) tma_load_2d(dst + 16384, &tm_lo, &a_full[st], 0, tile * 128);
+            }
+            __syncwarp();
+            if (++st == a.stages) { st = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        const uint32_t id16 = make_idesc_bf16(128, 16, ELT), id8 = make_idesc_e4m3(128, 16);
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        const uint64_t d_wh = make_smem_desc(smem_u32(w_hi), 16, 1024, 2), d_wl = make_smem_desc(smem_u32(w_lo), 16, 1024, 2);
+        const uint64_t d_w8 = make_smem_desc(smem_u32(w_8), 16, 512, 4);
+        int st = 0, ph = 0, it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int b = it % kP8Acc;
+            mbar_wait(&a_full[st], ph);
+            mbar_wait(&acc_empty[b], ((it / kP8Acc) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + (size_t)st * a.stage_bytes);
+            if (elect_one()) {
+                const uint64_t d_ah = make_smem_desc(a_addr, 16, 1024, 2);
+                const uint32_t d_t = tmem + (uint32_t)(b * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_t, d_ah + 2 * k, d_wh + 2 * k, id16, k ? 1u : 0u);
+                if (a.mode == 1) {
+                    const uint64_t d_al = make_smem_desc(a_addr + 16384, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(d_t, d_al + 2 * k, d_wh + 2 * k, id16, 1u);
+                }
+                if (a.mode != 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(d_t, d_ah + 2 * k, d_wl + 2 * k, id16, 1u);
+                }
+                if (a.mode == 2) {
+                    const uint64_t d_a8 = make_smem_desc(a_addr + 16384, 16, 512, 4);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_f8(d_t, d_a8 + 2 * k, d_w8 + 2 * k, id8, 1u);
+                }
+                umma_commit(&a_empty[st]);
+                umma_commit(&acc_full[b]);
+            }
+            __syncwarp();
+            if (++st == a.stages) { st = 0; ph ^= 1; }
+        }
+    } else {
+        const int grp = (warp - 2) >> 2, quad = warp & 3;
+        const int row = quad * 32 + lane;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { sc[c] = a.scale[c]; sh[c] = a.shift[c]; }
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < a.n_tiles; tile += kP8Groups * gridDim.x, it += kP8Groups) {
+            const int b = it % kP8Acc;
+            mbar_wait(&acc_full[b], (it / kP8Acc) & 1);
+            tc_fence_after();
+            uint32_t r[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * 16)) : "memory");
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[b]);      // the values are in registers: the accumulator may be overwritten
+            const long long p = (long long)tile * 128 + row;
+            if (p >= a.nplane) continue;
+            const int f = (int)(p % a.Fp);
+            if (f >= a.F) continue;
+            const size_t o0 = (size_t)(p / a.Fp) * a.ldx + f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float y = act_fast<ACT>(fmaf(__uint_as_float(r[c]), sc[c], sh[c]));
+                const size_t o = o0 + (size_t)c * a.F;
+                if (a.x32) a.x32[o] = y;
+                if (a.xhi) {
+                    elt16 yh, yl;
+                    split16<ELT>(y, yh, yl);
+                    a.xhi[o] = yh;
+                    if (a.xlo) a.xlo[o] = yl;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 64);
 }
 
 // fp32 plane [B][T][Fp][64] <-> bf16 hi/lo planes (debug hook)
@@ -684,6 +845,18 @@ __global__ void k_pack_conv_f8c(const float* __restrict__ w32, const unsigned in
     dst[ci] = (uint8_t)(pr & 0xff);
     dst[64 + ci] = (uint8_t)(pr >> 8);
 }
+// W8 fp32 [ci][8] -> rows [16 (8 used)][64 ci]: 16-bit hi / lo (rows 0..15 hi, 16..31 lo; bf16 and fp16 copies) and e4m3(2^-8 w_hi), scaled by s
+__global__ void k_pack_point8(const float* __restrict__ w32, const unsigned int* __restrict__ maxbits, elt16* __restrict__ wb, elt16* __restrict__ wh,
+                              uint8_t* __restrict__ w8) {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;     // 16 * 64
+    if (i >= 1024) return;
+    const int ci = i & 63, r = i >> 6;
+    const float v = r < 8 ? pow2_scale(*maxbits) * w32[ci * 8 + r] : 0.f;
+    split16<0>(v, wb[i], wb[1024 + i]);
+    split16<1>(v, wh[i], wh[1024 + i]);
+    w8[i] = (uint8_t)(e4m3x2(__half2float(__ushort_as_half(wh[i])) * (1.f / kF8cLoScale), 0.f) & 0xff);
+}
+
 __global__ void k_scale_tc(const float* __restrict__ scale, const unsigned int* __restrict__ maxbits, float* __restrict__ out, int n) {
     int i = threadIdx.x;
     if (i < n) out[i] = scale[i] / pow2_scale(*maxbits);
@@ -699,6 +872,9 @@ struct TcState {
     elt16* w_lo[2][8] = {};
     float* scale_tc[8] = {};  // BN scale divided by the layer's power-of-two weight scale
     uint8_t* w_c8[8] = {};    // VS_PREC_FP16_F8C: e4m3 correction tiles (k_pack_conv_f8c)
+    elt16* p8_w[2] = {};      // cnn8 on tensor cores: [elt][32 rows (16 hi, 16 lo)][64]
+    uint8_t* p8_w8 = nullptr; // its e4m3(2^-8 w_hi) tile [16][64]
+    int point8_mma = 1;       // VOICESPLIT_POINT8_MMA = 0 selects the CUDA-core cnn8 kernel
     elt16* wT_hi[2][8] = {};  // training: data-gradient weights (taps flipped, channels transposed), same tile format
     elt16* wT_lo[2][8] = {};
     float* unscale[8] = {};   // 64 copies of 1 / (power-of-two weight scale): epilogue scale of the raw-output convs
@@ -723,6 +899,7 @@ int tc_create(vs_engine* e) {
     if (const char* c = getenv("VOICESPLIT_CONV_TILE2D")) s->tile2d = s->tile2d_dgrad = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_TILE2D_DGRAD")) s->tile2d_dgrad = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_L2PREFETCH")) s->l2_prefetch = atoi(c) != 0;
+    if (const char* c = getenv("VOICESPLIT_POINT8_MMA")) s->point8_mma = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_CLUSTER")) {
         const int v = atoi(c);
         if (v == 1 || v == 2 || v == 4 || v == 8) s->cluster = v;
@@ -738,6 +915,7 @@ void tc_destroy(vs_engine* e) {
         for (int t = 0; t < 2; ++t) { cudaFree(s->w_hi[t][l]); cudaFree(s->w_lo[t][l]); cudaFree(s->wT_hi[t][l]); cudaFree(s->wT_lo[t][l]); }
         cudaFree(s->scale_tc[l]); cudaFree(s->unscale[l]); cudaFree(s->w_c8[l]);
     }
+    cudaFree(s->p8_w[0]); cudaFree(s->p8_w[1]); cudaFree(s->p8_w8);
     cudaFree(s->wmax);
     delete s;
     e->tc = nullptr;
@@ -773,6 +951,17 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
         k_pack_conv_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->conv_wT32[l], s->wmax + l, s->wT_hi[0][l], s->wT_lo[0][l],
                                                                     s->wT_hi[1][l], s->wT_lo[1][l], g.kh, g.kw, n_j, conv_pairs_rows(s, g, true) ? 1 : 0);
         k_scale_tc<<<1, 64, 0, st>>>(e->ones64, s->wmax + l, s->unscale[l], 64);
+    }
+    {   // cnn8 (64 -> 8, 1x1) as an MMA B operand
+        if (!s->p8_w[0]) {
+            VS_CUDA_TRY(cudaMalloc(&s->p8_w[0], 2048 * sizeof(elt16)));
+            VS_CUDA_TRY(cudaMalloc(&s->p8_w[1], 2048 * sizeof(elt16)));
+            VS_CUDA_TRY(cudaMalloc(&s->p8_w8, 1024));
+            VS_CUDA_TRY(cudaMalloc(&s->scale_tc[7], 64 * sizeof(float)));
+        }
+        k_absmax<<<2, 256, 0, st>>>(e->conv_w32[7], 512, s->wmax + 7);
+        k_pack_point8<<<4, 256, 0, st>>>(e->conv_w32[7], s->wmax + 7, s->p8_w[0], s->p8_w[1], s->p8_w8);
+        k_scale_tc<<<1, 64, 0, st>>>(e->conv_scale[7], s->wmax + 7, s->scale_tc[7], 8);
     }
     VS_CUDA_TRY(cudaGetLastError());
     int rc = tc_lstm_pack(e, &s->lstm, st);
@@ -966,6 +1155,42 @@ static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const e
                                     elt16* xhi, elt16* xlo, int ldx, int B, int T, cudaStream_t st) {
     const int F = e->d.num_freq, Fp = padded_freq(F);
     const long long nplane = (long long)B * T * Fp;
+    const TcState* s = (const TcState*)e->tc;
+    if (s->point8_mma && nplane < (1ll << 31) - 256) {
+        Point8Args a{};
+        a.mode = f8c ? 2 : (lo ? 1 : 0);
+        a.stage_bytes = a.mode == 0 ? 16384 : (a.mode == 1 ? 32768 : 24576);
+        a.stages = (s->max_smem - 1024 - 8192 - 512) / a.stage_bytes;
+        if (a.stages > 8) a.stages = 8;
+        a.n_tiles = (int)((nplane + 127) / 128);
+        a.nplane = nplane; a.F = F; a.Fp = Fp; a.ldx = ldx;
+        a.scale = s->scale_tc[7]; a.shift = e->conv_shift[7];
+        a.x32 = x32; a.xhi = xhi; a.xlo = xlo;
+        CUtensorMap tm_hi, tm_lo, tm_w16, tm_w8;
+        uint64_t pd[2] = {64, (uint64_t)nplane}, ps[1] = {128};
+        uint32_t pb[2] = {64, 128}, pb8[2] = {32, 128};
+        uint64_t wd[2] = {64, 32}, wd8[2] = {32, 16}, ws8[1] = {64};
+        uint32_t wb[2] = {64, 16}, wb8[2] = {32, 16};
+        bool ok = make_tmap_bf16(&tm_hi, (void*)hi, 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && (f8c ? make_tmap_bf16(&tm_lo, (void*)lo, 2, pd, ps, pb8, CU_TENSOR_MAP_SWIZZLE_64B)
+                        : make_tmap_bf16(&tm_lo, (void*)(lo ? lo : hi), 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B));
+        ok = ok && make_tmap_bf16(&tm_w16, s->p8_w[elt ? 1 : 0], 2, wd, ps, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_tmap_bf16(&tm_w8, s->p8_w8, 2, wd8, ws8, wb8, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (!ok) return cudaErrorInvalidValue;
+        const int smem = 1024 + 8192 + a.stages * a.stage_bytes + 512;
+        const unsigned grid = (unsigned)(a.n_tiles < e->num_sms ? a.n_tiles : e->num_sms);
+        const bool relu = e->d.activation == VS_ACT_RELU;
+#define VS_P8(A, E)                                                                                                          \
+    do {                                                                                                                     \
+        cudaError_t ce_ = cudaFuncSetAttribute(k_point8_mma<A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);        \
+        if (ce_ != cudaSuccess) return ce_;                                                                                  \
+        k_point8_mma<A, E><<<grid, kP8Threads, smem, st>>>(a, tm_hi, tm_lo, tm_w16, tm_w8);                                   \
+    } while (0)
+        if (relu) { if (elt || f8c) VS_P8(VS_ACT_RELU, 1); else VS_P8(VS_ACT_RELU, 0); }
+        else { if (elt || f8c) VS_P8(VS_ACT_MISH, 1); else VS_P8(VS_ACT_MISH, 0); }
+#undef VS_P8
+        return cudaGetLastError();
+    }
     const unsigned grid = (unsigned)((nplane + 255) / 256);
     const int smem = 2 * 256 * 144;
     const bool relu = e->d.activation == VS_ACT_RELU;

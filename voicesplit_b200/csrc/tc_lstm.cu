@@ -106,12 +106,14 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 const unsigned int target = (unsigned int)s * a.nslices;
                 unsigned int spins = 0;
                 const long long c0 = VS_CLK();
-                while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+                for (;;) {      // acquire loads: no separate gpu-scope fence (an extra L2 round trip) between the flag and the TMA issue
+                    unsigned int seen;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+                    if (seen >= target) break;
                     if (++spins > (1u << 28)) __trap();
                 }
                 const long long c1 = VS_CLK();
                 tm_spin += c1 - c0;
-                __threadfence();
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy flag read -> async-proxy (TMA) data reads
                 const int par = (s - 1) & 1;                       // buffer h_{s-1} was written to
                 const int row0 = ((d * 2 + par) * a.Bp) + grp * kLB;
@@ -242,24 +244,17 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 tm_math += c1 - c0;
                 c0 = c1;
             }
+            // h_t for the next step first: only these 64 bytes per utterance are on the critical path of the exchange.  The fp32
+            // lstm_out and the relu(h) planes of the FC head follow AFTER the release below - their (row-strided, half-sector)
+            // stores then drain while the other slices are still being waited for, instead of delaying this CTA's fence.
+            const bool fast = nu == kLU && (a.H & 7) == 0;
             if (valid) {
-                if (nu == kLU && (a.H & 7) == 0) {
+                if (fast) {
                     *reinterpret_cast<uint4*>(hx_hi) = *reinterpret_cast<const uint4*>(vh);
                     *reinterpret_cast<uint4*>(hx_hi + 8) = *reinterpret_cast<const uint4*>(vh + 8);
                     if (hx_lo) {
                         *reinterpret_cast<uint4*>(hx_lo) = *reinterpret_cast<const uint4*>(vl);
                         *reinterpret_cast<uint4*>(hx_lo + 8) = *reinterpret_cast<const uint4*>(vl + 8);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kLU; j += 4)
-                        *reinterpret_cast<float4*>(a.hout + oidx + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
-                    if (a.hr_hi) {
-                        *reinterpret_cast<uint4*>(a.hr_hi + oidx) = *reinterpret_cast<const uint4*>(rh);
-                        *reinterpret_cast<uint4*>(a.hr_hi + oidx + 8) = *reinterpret_cast<const uint4*>(rh + 8);
-                        if (a.hr_lo) {
-                            *reinterpret_cast<uint4*>(a.hr_lo + oidx) = *reinterpret_cast<const uint4*>(rl);
-                            *reinterpret_cast<uint4*>(a.hr_lo + oidx + 8) = *reinterpret_cast<const uint4*>(rl + 8);
-                        }
                     }
                 } else {
 #pragma unroll
@@ -267,8 +262,6 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                         if (j < nu) {
                             hx_hi[j] = vh[j];
                             if (hx_lo) hx_lo[j] = vl[j];
-                            a.hout[oidx + j] = hv[j];
-                            if (a.hr_hi) { a.hr_hi[oidx + j] = rh[j]; if (a.hr_lo) a.hr_lo[oidx + j] = rl[j]; }
                         }
                     }
                 }
@@ -288,6 +281,29 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                     atomicAdd(counter, 1u);
                 }
                 tm_bar += VS_CLK() - c0;
+            }
+            if (valid) {
+                if (fast) {
+#pragma unroll
+                    for (int j = 0; j < kLU; j += 4)
+                        *reinterpret_cast<float4*>(a.hout + oidx + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
+                    if (a.hr_hi) {
+                        *reinterpret_cast<uint4*>(a.hr_hi + oidx) = *reinterpret_cast<const uint4*>(rh);
+                        *reinterpret_cast<uint4*>(a.hr_hi + oidx + 8) = *reinterpret_cast<const uint4*>(rh + 8);
+                        if (a.hr_lo) {
+                            *reinterpret_cast<uint4*>(a.hr_lo + oidx) = *reinterpret_cast<const uint4*>(rl);
+                            *reinterpret_cast<uint4*>(a.hr_lo + oidx + 8) = *reinterpret_cast<const uint4*>(rl + 8);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kLU; ++j) {
+                        if (j < nu) {
+                            a.hout[oidx + j] = hv[j];
+                            if (a.hr_hi) { a.hr_hi[oidx + j] = rh[j]; if (a.hr_lo) a.hr_lo[oidx + j] = rl[j]; }
+                        }
+                    }
+                }
             }
         }
         if (TIMING && blockIdx.x == 0 && threadIdx.x == 64 && a.timing) { a.timing[4] = tm_acc; a.timing[5] = tm_math; a.timing[6] = tm_store; a.timing[7] = tm_bar; }
