@@ -7,6 +7,9 @@ import numpy as np
 import torch
 
 from voicesplit_b200 import synth
+if os.environ.get("VOICESPLIT_ALT_SO"):      # A/B against a library built from another commit (same ABI), tools only
+    from voicesplit_b200 import _cabi
+    _cabi.LIB_PATH = os.environ["VOICESPLIT_ALT_SO"]
 from voicesplit_b200.engine import MaskEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32

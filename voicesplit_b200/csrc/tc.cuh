@@ -55,6 +55,7 @@ struct GemmTcArgs {
     int tn;                     // 1: C[M][N] = sum_k A[k][m] * W[k][n] (both operands [K rows][cols], MN-major MMAs; N tile % 64 == 0)
     int n_tile, n_tiles_n, n_tiles_m, total_tiles, n_kb;
     int passes, stages;
+    int csz;                    // CTAs per cluster (1 or 2): pairs of M blocks share every W tile through TMA multicast (launch_gemm_tc decides)
     int group_rows;             // GATES: rows per utterance (T)
     const float* bias;          // [N] (FC1/FC2) or null
     const float* bias_group;    // [M / group_rows][N] (GATES)

@@ -61,6 +61,7 @@ struct ConvTcArgs {
     // (tr + kh - 1) x 8 block around it, loaded ONCE per plane with a 4-D TMA box and shared by all kh taps: tap dt is the window
     // starting dt * 8 rows (= dt swizzle atoms) into the strip.  Flat tiles would fetch a fresh strip per tap (7x the bytes).
     int tile2d, tr, n_ft, T;
+    unsigned int n_ft_magic;   // 2^32 / n_ft + 1: tin / n_ft as a multiply-high (tin < tiles per utterance)
     int tr_out, t_halo;   // 2-D tiles: output frames per tile (tr - 1: the upper tap of a pair lands one frame up), (kh - 1) / 2
     int l2_prefetch;      // flat tiles: prefetch the next tile's strips into L2 (VOICESPLIT_CONV_L2PREFETCH=1; off by default: measured no gain)
     int act;
@@ -256,46 +257,44 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                         for (int sp = 0; sp < n_strip_loads; ++sp) s_desc[sp] += (16 * 128) >> 4;   // next tap pair: 2 frames = 16 rows down
                     }
                     for (int j = 0; j < a.n_j; ++j) {
-                        // the weight tiles of this step (W_hi, then W_lo / the e4m3 correction tile) sit in consecutive ring slots:
-                        // wait for all of them, then ONE elected issue block per step
-                        int wsl[2];
-                        for (int wp = 0; wp < n_strip_loads; ++wp) {
-                            mbar_wait(&w_full[ws], wph);
-                            wsl[wp] = ws;
-                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
-                        }
+                        // One wait + one elected issue block PER weight tile, written out twice (not a loop: the compiler then keeps two
+                        // straight-line blocks of four MMAs).  The MMAs on W_hi start while the second tile of the step - fetched by the
+                        // other CTA of the cluster - may still be in flight; waiting for both tiles first cost 5 % more cycles per
+                        // 5x5 layer, a predicated loop over the two tiles 38 % (same-box A/B, profiles/r02_conv_issue_loop_ab.txt).
+                        const uint64_t b0 = s_desc[0] + (uint64_t)(16 * j);      // window start 2 j pixel rows further: 2 j * 128 B >> 4
+                        const uint64_t b1 = s_desc[1] + (uint64_t)(16 * j);
+                        mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t b0 = s_desc[0] + (uint64_t)(16 * j);      // window start 2 j pixel rows further: 2 j * 128 B >> 4
-                            const uint64_t a0 = w_desc0 + (uint64_t)(wsl[0] * (kWTileBytes >> 4));
-                            if (F8C) {
-                                // W_hi x S_hi as four kind::f16 MMAs (K = 16), then the e4m3 correction tile x the c8 strip as four
-                                // kind::f8f6f4 MMAs (K = 32 bytes each): x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
-                                const uint64_t b1 = s_desc[1] + (uint64_t)(16 * j);
-                                const uint64_t a1 = w_desc0 + (uint64_t)(wsl[1] * (kWTileBytes >> 4));
+                            const uint64_t a0 = w_desc0 + (uint64_t)(ws * (kWTileBytes >> 4));
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k == 0 ? accumulate : 1u);
-                                if (a.csz > 1) umma_commit_mc(&w_empty[wsl[0]], cmask); else umma_commit(&w_empty[wsl[0]]);
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                            if (!F8C && n_strip_loads == 2) {      // hi*hi + lo*hi: W_hi against both strips
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f8(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc8, 1);
-                                if (a.csz > 1) umma_commit_mc(&w_empty[wsl[1]], cmask); else umma_commit(&w_empty[wsl[1]]);
-                            } else {
-                                // W_hi x (S_hi, S_lo), then W_lo x S_hi  (hi*hi + lo*hi + hi*lo); single-pass modes: W_hi x S_hi only
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k == 0 ? accumulate : 1u);
-                                if (n_strip_loads == 2) {
-                                    const uint64_t b1 = s_desc[1] + (uint64_t)(16 * j);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);
-                                }
-                                if (a.csz > 1) umma_commit_mc(&w_empty[wsl[0]], cmask); else umma_commit(&w_empty[wsl[0]]);
-                                if (n_strip_loads == 2) {
-                                    const uint64_t a1 = w_desc0 + (uint64_t)(wsl[1] * (kWTileBytes >> 4));
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1);
-                                    if (a.csz > 1) umma_commit_mc(&w_empty[wsl[1]], cmask); else umma_commit(&w_empty[wsl[1]]);
-                                }
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);
                             }
+                            if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
+                        }
+                        __syncwarp();
+                        if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        if (n_strip_loads == 2) {
+                            mbar_wait(&w_full[ws], wph);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t a1 = w_desc0 + (uint64_t)(ws * (kWTileBytes >> 4));
+                                if (F8C) {
+                                    // the e4m3 correction tile x the c8 strip as four kind::f8f6f4 MMAs (K = 32 bytes each):
+                                    // x_lo*w_hi over bytes 0..63, x_hi*w_lo over bytes 64..127
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_f8(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc8, 1);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1);     // hi*lo: W_lo x S_hi
+                                }
+                                if (a.csz > 1) umma_commit_mc(&w_empty[ws], cmask); else umma_commit(&w_empty[ws]);
+                            }
+                            __syncwarp();
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                         __syncwarp();
                         accumulate = 1;
@@ -327,17 +326,23 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
         const int codd = (lane >> 1) & 1;
         const size_t row_px = T2D ? (size_t)a.Fp : 0;    // 2-D tiles: pixels between consecutive frames
         int it = 0;
+        // tile = (utterance b, tile tin inside it), advanced without divisions: on the 2-D layer every warp handles ONE chunk per tile,
+        // so per-tile bookkeeping is not amortised (two integer divisions were 14 % of the epilogue's samples, r02 cnn2 capture)
+        int b = (int)blockIdx.x / a.tiles_per_utt, tin = (int)blockIdx.x - b * a.tiles_per_utt;
+        const int step_b = (int)gridDim.x / a.tiles_per_utt, step_t = (int)gridDim.x - step_b * a.tiles_per_utt;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, aph = (it >> 1) & 1;
-            const int b = tile / a.tiles_per_utt;
-            const int tin = tile - b * a.tiles_per_utt;
             int q0 = 0, t0 = 0, f0 = 0;                  // flat: first pixel; 2-D: first frame / bin (column p = frame t0 + p / 8, bin f0 + p % 8)
-            if (T2D) { const int tt = tin / a.n_ft; t0 = tt * a.tr_out; f0 = (tin - tt * a.n_ft) * 8; }
-            else q0 = tin * useful;
+            if (T2D) {
+                const int tt = (int)(((unsigned long long)(unsigned)tin * a.n_ft_magic) >> 32);     // tin / n_ft
+                t0 = tt * a.tr_out; f0 = (tin - tt * a.n_ft) * 8;
+            } else q0 = tin * useful;
+            const size_t plane0 = (size_t)b * a.Q;       // first pixel of the utterance's plane
+            tin += step_t; b += step_b;
+            if (tin >= a.tiles_per_utt) { tin -= a.tiles_per_utt; ++b; }
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.N);
-            const size_t plane0 = (size_t)b * a.Q;       // first pixel of the utterance's plane
             for (int c0 = cgrp * 32; c0 < a.N; c0 += 32 * (EW / 4)) {
                 uint32_t r[32];
                 uint32_t nxt = 0;                         // flat: column c0 + 32 (the upper tap of the chunk's last pixel)
@@ -354,15 +359,17 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                 size_t px0;
                 bool interior;
                 int f = 0;
+                // columns of this chunk that are output pixels of the tile (the last chunk is cut by the tap-pair shift: 31 flat, 24 2-D)
+                const int ncols = useful - c0 < 32 ? useful - c0 : 32;
                 if (T2D) {
                     const int tr0 = t0 + (c0 >> 3);       // the chunk covers frames tr0 .. tr0 + 3, bins f0 .. f0 + 7
                     px0 = (size_t)tr0 * a.Fp + f0 + h;
-                    interior = tr0 + 4 <= a.T && f0 + 8 <= a.F && c0 + 32 <= useful;
+                    interior = tr0 + (ncols >> 3) <= a.T && f0 + 8 <= a.F;
                 } else {
                     px0 = (size_t)q0 + c0 + h;
                     const int fc = (q0 + c0) % a.Fp;      // bin of the chunk's first column; rows are Fp pixels, bins >= F are padding
                     f = fc + h; if (f >= a.Fp) f -= a.Fp;
-                    interior = fc + 33 <= a.F && c0 + 32 <= useful && q0 + c0 + 32 <= a.Q;
+                    interior = fc + 33 <= a.F && q0 + c0 + 32 <= a.Q;
                 }
                 elt16* ohi = OUT32 ? nullptr : a.out_hi + (plane0 + px0) * 64 + (co & ~1);
                 elt16* olo = want_lo ? a.out_lo + (plane0 + px0) * 64 + (co & ~1) : nullptr;
@@ -375,10 +382,12 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                     if (F8C) oc8 += lane_px * 128;
                 }
                 tmem_ld_wait();
-                auto body = [&](auto fast_tag) {
-                    constexpr bool FAST = decltype(fast_tag)::value;
+                // FAST: no padding bin, plane edge or frame edge in the chunk; FULL: all 32 columns are output pixels (else the first ncols)
+                auto body = [&](auto fast_tag, auto full_tag) {
+                    constexpr bool FAST = decltype(fast_tag)::value, FULL = decltype(full_tag)::value;
 #pragma unroll
                     for (int m = 0; m < 16; m += 2) {
+                        if (FAST && !FULL && 2 * m >= ncols) break;     // warp-uniform: the cut chunk stops early
                         float y[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -408,7 +417,8 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                         // pixel offset (from px0) of value mm: flat 2 mm; 2-D (mm / 4) frames + 2 (mm % 4) bins - compile-time but for Fp
                         auto off = [&](int mm) { return T2D ? (size_t)(mm >> 2) * row_px + 2 * (mm & 3) : (size_t)(2 * mm); };
                         auto valid = [&](int mm) {
-                            if (FAST) return true;
+                            if (FAST && FULL) return true;
+                            if (FAST) return 2 * mm + (T2D ? 0 : h) < ncols;
                             if (T2D) return c0 + 2 * mm < useful && t0 + ((c0 + 2 * mm) >> 3) < a.T;   // bins: every tile covers 8 in-plane bins
                             const int p = c0 + 2 * mm + h;
                             return p < useful && q0 + p < a.Q;
@@ -442,7 +452,8 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                         }
                     }
                 };
-                if (interior) body(std::true_type{}); else body(std::false_type{});
+                if (interior) { if (ncols == 32) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{}); }
+                else body(std::false_type{}, std::false_type{});
             }
             tc_fence_before();
             __syncwarp();
@@ -609,7 +620,8 @@ __global__ void __launch_bounds__(256) k_point8_tc(const elt16* __restrict__ hi,
 //   mode 0  one 16-bit pass              a_hi * w_hi
 //   mode 1  split operands, 3 passes     a_hi * w_hi + a_lo * w_hi + a_hi * w_lo
 //   mode 2  VS_PREC_FP16_F8C             a_hi * w_hi + a_hi * w_lo (both kind::f16: the weight tile is 2 KB, a second fp16 pass costs nothing
-//                                        here) + l8 * e4m3(2^-8 w_hi) over the 64-byte l8 half of the c8 row (x8 is not read: 192 B / pixel)
+//                                        here) + l8 * (e4m3(2^-8 w_hi) + e4m3 of its rounding residual) over the 64-byte l8 half of the
+//                                        c8 row (x8 is not read: 192 B / pixel)
 // Warp 0: TMA producer (ring of pixel tiles), warp 1: MMA issuer (4 accumulators of 16 TMEM columns), warps 2..13: three epilogue
 // groups of 4 warps (thread = one pixel x 8 channels: BN + act, 16-bit hi / lo of the LSTM operand at column c * F + f).
 // ---------------------------------------------------------------------------------------------
@@ -632,7 +644,8 @@ __global__ void __launch_bounds__(kP8Threads, 1) k_point8_mma(const Point8Args a
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* w_hi = smem;                 // [16 rows][128 B] 128B swizzle
     uint8_t* w_lo = smem + 2048;
-    uint8_t* w_8 = smem + 4096;           // [16 rows][64 B] e4m3, 64B swizzle
+    uint8_t* w_8 = smem + 4096;           // [16 rows][64 B] e4m3(2^-8 w_hi), 64B swizzle
+    uint8_t* w_8b = smem + 5120;          // the same for the e4m3 rounding residual of that tile (weight error 2^-8 instead of 2^-4)
     uint8_t* ring = smem + 8192;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * a.stage_bytes);
     uint64_t* a_full = bars;
@@ -656,10 +669,10 @@ __global__ void __launch_bounds__(kP8Threads, 1) k_point8_mma(const Point8Args a
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(w_full, 4096u + (a.mode == 2 ? 1024u : 0u));
+            mbar_arrive_expect_tx(w_full, 4096u + (a.mode == 2 ? 2048u : 0u));
             tma_load_2d(w_hi, &tm_w16, w_full, 0, 0);
             tma_load_2d(w_lo, &tm_w16, w_full, 0, 16);
-            if (a.mode == 2) tma_load_2d(w_8, &tm_w8, w_full, 0, 0);
+            if (a.mode == 2) { tma_load_2d(w_8, &tm_w8, w_full, 0, 0); tma_load_2d(w_8b, &tm_w8, w_full, 0, 16); }
         }
         __syncwarp();
         int st = 0, ph = 0;
@@ -679,7 +692,7 @@ __global__ void __launch_bounds__(kP8Threads, 1) k_point8_mma(const Point8Args a
         mbar_wait(w_full, 0);
         tc_fence_after();
         const uint64_t d_wh = make_smem_desc(smem_u32(w_hi), 16, 1024, 2), d_wl = make_smem_desc(smem_u32(w_lo), 16, 1024, 2);
-        const uint64_t d_w8 = make_smem_desc(smem_u32(w_8), 16, 512, 4);
+        const uint64_t d_w8 = make_smem_desc(smem_u32(w_8), 16, 512, 4), d_w8b = make_smem_desc(smem_u32(w_8b), 16, 512, 4);
         int st = 0, ph = 0, it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
             const int b = it % kP8Acc;
@@ -704,7 +717,10 @@ __global__ void __launch_bounds__(kP8Threads, 1) k_point8_mma(const Point8Args a
                 if (a.mode == 2) {
                     const uint64_t d_a8 = make_smem_desc(a_addr + 16384, 16, 512, 4);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_f8(d_t, d_a8 + 2 * k, d_w8 + 2 * k, id8, 1u);
+                    for (int k = 0; k < 2; ++k) {
+                        umma_f8(d_t, d_a8 + 2 * k, d_w8 + 2 * k, id8, 1u);
+                        umma_f8(d_t, d_a8 + 2 * k, d_w8b + 2 * k, id8, 1u);
+                    }
                 }
                 umma_commit(&a_empty[st]);
                 umma_commit(&acc_full[b]);
@@ -854,7 +870,10 @@ __global__ void k_pack_point8(const float* __restrict__ w32, const unsigned int*
     const float v = r < 8 ? pow2_scale(*maxbits) * w32[ci * 8 + r] : 0.f;
     split16<0>(v, wb[i], wb[1024 + i]);
     split16<1>(v, wh[i], wh[1024 + i]);
-    w8[i] = (uint8_t)(e4m3x2(__half2float(__ushort_as_half(wh[i])) * (1.f / kF8cLoScale), 0.f) & 0xff);
+    const float t = __half2float(__ushort_as_half(wh[i])) * (1.f / kF8cLoScale);
+    const unsigned int q = e4m3x2(t, 0.f) & 0xffu;
+    w8[i] = (uint8_t)q;
+    w8[1024 + i] = (uint8_t)(e4m3x2(t - e4m3_to_float(q), 0.f) & 0xffu);     // second tile: what the first rounding lost
 }
 
 __global__ void k_scale_tc(const float* __restrict__ scale, const unsigned int* __restrict__ maxbits, float* __restrict__ out, int n) {
@@ -956,7 +975,7 @@ int tc_pack(vs_engine* e, cudaStream_t st) {
         if (!s->p8_w[0]) {
             VS_CUDA_TRY(cudaMalloc(&s->p8_w[0], 2048 * sizeof(elt16)));
             VS_CUDA_TRY(cudaMalloc(&s->p8_w[1], 2048 * sizeof(elt16)));
-            VS_CUDA_TRY(cudaMalloc(&s->p8_w8, 1024));
+            VS_CUDA_TRY(cudaMalloc(&s->p8_w8, 2048));
             VS_CUDA_TRY(cudaMalloc(&s->scale_tc[7], 64 * sizeof(float)));
         }
         k_absmax<<<2, 256, 0, st>>>(e->conv_w32[7], 512, s->wmax + 7);
@@ -1031,6 +1050,7 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
         a.n_dt = (g.kh + 1) / 2; a.n_j = 1;
         a.N = 8 * a.tr;
         a.n_ft = Fp / 8;
+        a.n_ft_magic = (unsigned int)((1ull << 32) / (unsigned)a.n_ft + 1);
         a.tiles_per_utt = a.n_ft * ((T + a.tr_out - 1) / a.tr_out);
         a.total_tiles = B * a.tiles_per_utt;
     }
@@ -1169,7 +1189,7 @@ static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const e
         CUtensorMap tm_hi, tm_lo, tm_w16, tm_w8;
         uint64_t pd[2] = {64, (uint64_t)nplane}, ps[1] = {128};
         uint32_t pb[2] = {64, 128}, pb8[2] = {32, 128};
-        uint64_t wd[2] = {64, 32}, wd8[2] = {32, 16}, ws8[1] = {64};
+        uint64_t wd[2] = {64, 32}, wd8[2] = {32, 32}, ws8[1] = {64};
         uint32_t wb[2] = {64, 16}, wb8[2] = {32, 16};
         bool ok = make_tmap_bf16(&tm_hi, (void*)hi, 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B);
         ok = ok && (f8c ? make_tmap_bf16(&tm_lo, (void*)lo, 2, pd, ps, pb8, CU_TENSOR_MAP_SWIZZLE_64B)

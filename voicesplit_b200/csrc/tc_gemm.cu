@@ -19,6 +19,7 @@
 // next chunk runs in the other buffer - the "promotion" FP8 GEMMs use, for the same reason.
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace vs {
 using namespace ptx;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < nst; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < nst; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.csz); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGemmEpiWarps); }
         fence_barrier_init();
         prefetch_tensormap(&tm_a_hi); prefetch_tensormap(&tm_w_hi);
@@ -58,14 +59,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
     }
     tc_fence_before();
     __syncthreads();
+    if (a.csz > 1) cluster_sync_all();     // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Work items: (group of csz consecutive M blocks, N block); the CTAs of a cluster take the M blocks of one item, so every W tile
+    // (the larger operand: n_tile x 64 against 128 x 64) is fetched from L2 once per cluster - each CTA loads 1/csz of its rows and
+    // multicasts them.  The input projection is bound by L2 -> SM throughput (profiles/r02_ncu_gates_*), not by the tensor pipe.
+    const int crank = a.csz > 1 ? (int)cluster_ctarank() : 0;
+    const int n_items = ((a.n_tiles_m + a.csz - 1) / a.csz) * a.n_tiles_n;
+    const int item0 = blockIdx.x / a.csz, item_step = gridDim.x / a.csz;
+    const uint16_t cmask = (uint16_t)((1u << a.csz) - 1);
 
     if (warp == 0) {
         {   // producer: whole warp waits (warp-uniform), one elected lane issues the TMA loads
             int st = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
+            const int w_rows = a.n_tile / a.csz;       // W rows this CTA fetches (for every CTA of the cluster)
+            for (int item = item0; item < n_items; item += item_step) {
+                const int mg = item / a.n_tiles_n, nb = item - mg * a.n_tiles_n;
+                const int mb = mg * a.csz + crank;
                 for (int kb = 0; kb < a.n_kb; ++kb) {
                     mbar_wait(&empty[st], ph ^ 1);
                     if (elect_one()) {
@@ -82,6 +93,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                             if (nplanes == 2)
                                 tma_load_2d(dst + nplanes * a_bytes + w_bytes_al + jb * 8192, &tm_w_lo, &full[st], nb * a.n_tile + jb * 64, kb * 64);
                         }
+                    } else if (a.csz > 1) {
+                        tma_load_2d(dst, &tm_a_hi, &full[st], kb * 64, mb * 128);
+                        if (nplanes == 2) tma_load_2d(dst + a_bytes, &tm_a_lo, &full[st], kb * 64, mb * 128);
+                        uint8_t* wdst = dst + nplanes * a_bytes + (size_t)crank * w_rows * 128;
+                        tma_load_2d_mc(wdst, &tm_w_hi, &full[st], kb * 64, nb * a.n_tile + crank * w_rows, cmask);
+                        if (nplanes == 2) tma_load_2d_mc(wdst + w_bytes_al, &tm_w_lo, &full[st], kb * 64, nb * a.n_tile + crank * w_rows, cmask);
                     } else {
                         tma_load_2d(dst, &tm_a_hi, &full[st], kb * 64, mb * 128);
                         if (nplanes == 2) tma_load_2d(dst + a_bytes, &tm_a_lo, &full[st], kb * 64, mb * 128);
@@ -102,7 +119,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
             const uint32_t idesc = make_idesc_bf16(128, a.n_tile, ELT) | (a.tn ? ((1u << 15) | (1u << 16)) : 0u);
             const uint32_t kstep16 = a.tn ? (2048u >> 4) : (32u >> 4), lbo = a.tn ? 8192u : 16u;   // K step in descriptor address units
             int st = 0, ph = 0, cc = 0;   // cc: chunk counter across tiles (TMEM buffer = cc & 1)
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int item = item0; item < n_items; item += item_step) {
                 for (int kb0 = 0; kb0 < a.n_kb; kb0 += kChunkKb, ++cc) {
                     const int buf = cc & 1, aph = (cc >> 1) & 1;
                     mbar_wait(&acc_empty[buf], aph ^ 1);
@@ -127,7 +144,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                                     umma_bf16(d_tmem, d_ah + o, d_wl + o, idesc, 1);
                                 }
                             }
-                            umma_commit(&empty[st]);
+                            // the stage is free once BOTH CTAs of the cluster have consumed it: the peer multicasts into it too
+                            if (a.csz > 1) umma_commit_mc(&empty[st], cmask); else umma_commit(&empty[st]);
                         }
                         __syncwarp();
                         accumulate = 1;
@@ -144,8 +162,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
         constexpr int kColStep = 32 * (kGemmEpiWarps / 4);      // this warp takes columns cgrp*32 + i*kColStep .. +32
         constexpr int kMaxCols = 256 / kColStep;                // at most 4 column chunks per warp
         int cc = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            const int mb = tile / a.n_tiles_n, nb = tile - mb * a.n_tiles_n;
+        for (int item = item0; item < n_items; item += item_step) {
+            const int mg = item / a.n_tiles_n, nb = item - mg * a.n_tiles_n;
+            const int mb = mg * a.csz + crank;
             const int m = mb * 128 + quad * 32 + lane;
             const int n0 = nb * a.n_tile;
             float acc[kMaxCols][32];
@@ -338,6 +357,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
     }
     tc_fence_before();
     __syncthreads();
+    if (a.csz > 1) cluster_sync_all();     // nobody leaves while the peer may still multicast into its shared memory / barriers
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -391,6 +411,7 @@ struct GemmState {
     elt16 *fc2_hi[2] = {}, *fc2_lo[2] = {};  // [F][N1]
     elt16 *wihT_hi = nullptr, *wihT_lo = nullptr;   // training: W_ih[:, :8F]^T as [8F][8H] bf16 (operand of dX = da W_ih)
     int max_smem = 0;
+    int cluster = 2;      // VOICESPLIT_GEMM_CLUSTER = 1 disables the W-tile multicast pairs
 };
 static GemmState* g_state(vs_engine* e);
 
@@ -474,13 +495,15 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     a.n_tiles_m = (a.M + 127) / 128;
     a.total_tiles = a.n_tiles_m * a.n_tiles_n;
     a.n_kb = (a.K + 63) / 64;
+    // pairs of M blocks share their W tiles through TMA multicast when there is enough work for every cluster (the large GEMMs)
+    a.csz = (g->cluster > 1 && !a.tn && a.n_tile % 16 == 0 && a.total_tiles >= 2 * e->num_sms) ? 2 : 1;
     if (a.lda % 8 || a.ldw % 8) { set_error("tensor-core GEMM needs 16-byte aligned operand rows (lstm_dim % 4 == 0)"); return VS_ERR_INVALID; }
     CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
     {
         uint64_t ad[2] = {(uint64_t)a.K, (uint64_t)a.M}, as[1] = {(uint64_t)a.lda * sizeof(elt16)};
         uint32_t ab[2] = {64, 128};
         uint64_t wd[2] = {(uint64_t)a.K, (uint64_t)a.N}, ws[1] = {(uint64_t)a.ldw * sizeof(elt16)};
-        uint32_t wb[2] = {64, (uint32_t)a.n_tile};
+        uint32_t wb[2] = {64, (uint32_t)(a.n_tile / a.csz)};
         if (a.tn) {   // [K rows][cols] operands: inner dimension = output rows / cols, boxes of 64 x 64
             ad[0] = (uint64_t)a.M; ad[1] = (uint64_t)a.K; ab[1] = 64;
             wd[0] = (uint64_t)a.N; wd[1] = (uint64_t)a.K; wb[1] = 64;
@@ -499,12 +522,20 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     if (a.stages > 6) a.stages = 6;
     if (a.stages < 2) { set_error("gemm tile does not fit shared memory"); return VS_ERR_UNSUPPORTED; }
     const int smem = 1024 + a.stages * stage_bytes + 512 + epi_scratch;
-    const int grid = a.total_tiles < e->num_sms ? a.total_tiles : e->num_sms;
+    const int n_items = (a.n_tiles_m + a.csz - 1) / a.csz * a.n_tiles_n;
+    const int max_clusters = e->num_sms / a.csz;
+    const int grid = (n_items < max_clusters ? n_items : max_clusters) * a.csz;
     cudaError_t ce = cudaSuccess;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = a.csz > 1 ? 1 : 0;
 #define VS_GEMM_TC(E, L)                                                                                   \
     do {                                                                                                   \
         ce = cudaFuncSetAttribute(k_gemm_tc<E, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
-        if (ce == cudaSuccess) k_gemm_tc<E, L><<<grid, kGemmThreads, smem, st>>>(a, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo); \
+        if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_gemm_tc<E, L>, a, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo); \
     } while (0)
     if (epi == GEPI_PLAIN) { if (elt) VS_GEMM_TC(GEPI_PLAIN, 1); else VS_GEMM_TC(GEPI_PLAIN, 0); }
     else if (epi == GEPI_STFT) { if (elt) VS_GEMM_TC(GEPI_STFT, 1); else VS_GEMM_TC(GEPI_STFT, 0); }
@@ -645,6 +676,7 @@ static GemmState* g_state(vs_engine* e) {
     if (!hdr->gemm) {
         GemmState* g = new GemmState();
         cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+        if (const char* c = getenv("VOICESPLIT_GEMM_CLUSTER")) g->cluster = atoi(c) == 1 ? 1 : 2;
         hdr->gemm = g;
     }
     return (GemmState*)hdr->gemm;
