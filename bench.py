@@ -346,7 +346,8 @@ def main():
                     pj = json.load(open(prof))
                     if pj.get("precision") == prec and pj.get("frames") == T and pj.get("freq_bins") == F:
                         traffic = pj["dram_bytes_per_launch"] / pj["batch"] * B
-                        traffic_src = f"profiles/{name} (ncu --set full at B = {pj['batch']}, scaled per utterance)"
+                        traffic_src = (f"profiles/{name} (ncu at B = {pj['batch']}: dram__bytes_read + dram__bytes_write, mean over the five 5x5 "
+                                       "launches of one forward, scaled per utterance)")
                         break
             roof = {"bound": "tensor", "kernel": "k_conv_tc: dilated 5x5 conv 64->64 + BN + act (cnn3..cnn7)", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
