@@ -165,6 +165,41 @@ def test_batch_independence_and_host_entry():
         assert torch.equal(mh, full.cpu())
 
 
+@pytest.mark.parametrize("B,groups_per_cta", [(130, 1), (385, 1), (130, 2), (257, 2), (385, 2)])
+def test_recurrence_with_several_utterance_groups(B, groups_per_cta):
+    """More than 128 utterances: several groups of 128 per launch, one per CTA (default) or two per CTA (the experiment knob: each
+    group with its own accumulator, cell warps and exchange barrier; beyond 256 a second / half-filled set) - utterances of every
+    group must equal their single-utterance run, and the whole batch the fp32 path.  The knob is read once per process, so the
+    two-group cases run in a child process."""
+    if groups_per_cta == 2:
+        import subprocess, sys, os
+        env = dict(os.environ, VOICESPLIT_LSTM_GROUPS_PER_CTA="2")
+        code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
+                "t._several_groups_body(%d)" % (os.path.dirname(os.path.abspath(__file__)),
+                                                os.path.dirname(os.path.dirname(os.path.abspath(__file__))), B))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    _several_groups_body(B)
+
+
+def _several_groups_body(B):
+    dims = synth.make_dims(17, 8, 40, 24)        # 40 hidden units: three slices of 16, the last one partial
+    sd = synth.make_state_dict(dims, 9, "stress")
+    eng = MaskEngine(activation="mish", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    x, emb = synth.make_inputs(B, 23, dims, 4)
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
+    ref = eng.forward(xt, et, precision="fp32")
+    for precision in ("fp16x3", "bf16x3", "fp16_f8c", "fp16"):
+        full = eng.forward(xt, et, precision=precision)
+        torch.cuda.synchronize()
+        assert (full - ref).abs().max() < TOL_MAX[precision]
+        for b in (0, 127, 128, B - 1):
+            one = eng.forward(xt[b:b + 1], et[b:b + 1], precision=precision)
+            assert torch.allclose(full[b:b + 1], one, atol=2e-6, rtol=0), (precision, b)
+
+
 def test_abi_error_paths():
     """Errors surface as codes + messages, never as silent fallbacks."""
     import ctypes

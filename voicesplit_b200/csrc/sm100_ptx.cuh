@@ -218,7 +218,8 @@ inline PFN_tmapEncodeTiled get_tmap_encode() {
 }
 // rank-`rank` tensor of 16-bit elements (bf16 or fp16: TMA only moves the bits); dims/strides innermost first, strides[i] = byte stride of dim i+1
 inline bool make_tmap_bf16(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box, CUtensorMapSwizzle swz) {
+                           const uint32_t* box, CUtensorMapSwizzle swz,
+                           CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
     PFN_tmapEncodeTiled enc = get_tmap_encode();
     if (!enc) return false;
     cuuint64_t gd[5], gs[5];
@@ -226,7 +227,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, void* base, int rank, const uint64_
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 

@@ -1192,7 +1192,8 @@ static cudaError_t launch_point8_tc(const vs_engine* e, const elt16* hi, const e
         uint64_t wd[2] = {64, 32}, wd8[2] = {32, 32}, ws8[1] = {64};
         uint32_t wb[2] = {64, 16}, wb8[2] = {32, 16};
         bool ok = make_tmap_bf16(&tm_hi, (void*)hi, 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B);
-        ok = ok && (f8c ? make_tmap_bf16(&tm_lo, (void*)lo, 2, pd, ps, pb8, CU_TENSOR_MAP_SWIZZLE_64B)
+        // the l8 half is 64 of the 128 bytes of a c8 row: no L2 sector promotion, or the x8 half is fetched from DRAM as well
+        ok = ok && (f8c ? make_tmap_bf16(&tm_lo, (void*)lo, 2, pd, ps, pb8, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE)
                         : make_tmap_bf16(&tm_lo, (void*)(lo ? lo : hi), 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B));
         ok = ok && make_tmap_bf16(&tm_w16, s->p8_w[elt ? 1 : 0], 2, wd, ps, wb, CU_TENSOR_MAP_SWIZZLE_128B);
         ok = ok && make_tmap_bf16(&tm_w8, s->p8_w8, 2, wd8, ws8, wb8, CU_TENSOR_MAP_SWIZZLE_64B);

@@ -1,6 +1,6 @@
 // BiLSTM recurrence on tensor cores (reference nn.LSTM, models/voicesplit/model.py:57-61,82).
 //
-// Persistent kernel, one CTA per (direction, slice of 16 hidden units, group of 128 utterances).
+// Persistent kernel, one CTA per (direction, slice of 16 hidden units, set of 1 or 2 groups of 128 utterances).
 // The CTA keeps its 64 rows of W_hh (4 gates x 16 units, K = H) resident in shared memory as 16-bit
 // hi/lo planes for the whole sequence.  Every step it
 //   1. TMA-loads h_{t-1} of its 128 utterances ([128][H] hi/lo, written by the CTAs of the other
@@ -11,6 +11,10 @@
 //   4. writes h_t (16-bit hi/lo exchange buffer for the next step, fp32 lstm_out, and relu(h) hi/lo
 //      for the FC head) and arrives on the per-(direction, group) barrier.
 // The CTAs of one (direction, group) meet at that barrier once per step; nothing else is shared.
+// Optionally two groups per CTA (VOICESPLIT_LSTM_GROUPS_PER_CTA=2): independent recurrences over the same resident W slice,
+// taken in turn by the producer and the MMA issuer, each with its own accumulator, cell warps and barrier.  Meant to hide one
+// group's exchange (stores -> release -> the other slices' arrivals -> acquire -> TMA) under the other group's MMAs; measured
+// slower than one group per CTA on twice the SMs (see tc_lstm_recurrence), kept as an experiment knob and tested.
 #include "tc.cuh"
 #include "sm100_ptx.cuh"
 #include <stdlib.h>
@@ -21,9 +25,10 @@ using namespace ptx;
 constexpr int kLU = 16;         // hidden units per CTA
 constexpr int kLB = 128;        // utterances per CTA (MMA M)
 constexpr int kLStages = 3;     // h K-blocks in flight
+constexpr int kLGroups = 2;     // utterance groups per CTA at most
 
 struct LstmTcArgs {
-    int B, T, H, nslices, ngroups, group0, nkb, nk16, passes;
+    int B, T, H, nslices, nsets, gpc, group0, nkb, nk16, passes;   // nsets CTA sets of gpc (1 or 2) groups each, first group = group0
     int Bp;                       // utterance rows of the exchange buffer (multiple of 128)
     int Hp;                       // row stride of the exchange buffer (elements, multiple of 8)
     const float* gates_x;         // [B*T][8H]
@@ -45,7 +50,7 @@ struct LstmTcArgs {
 // kernel, enabled with VOICESPLIT_LSTM_TIMING=1 (tools/lstm_timing.py)
 #define VS_CLK() (TIMING ? clock64() : 0ll)
 template <int ELT, bool TIMING>
-__global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __grid_constant__ CUtensorMap tm_w_hi,
+__global__ void __launch_bounds__(64 + 128 * kLGroups, 1) k_lstm_tc(const LstmTcArgs a, const __grid_constant__ CUtensorMap tm_w_hi,
                                                     const __grid_constant__ CUtensorMap tm_w_lo,
                                                     const __grid_constant__ CUtensorMap tm_h_hi,
                                                     const __grid_constant__ CUtensorMap tm_h_lo) {
@@ -59,26 +64,27 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + kLStages;
     uint64_t* w_full = a_empty + kLStages;
-    uint64_t* acc_full = w_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* acc_full = w_full + 1;                                   // [kLGroups]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + kLGroups);
 
     // CTA coordinates
     int cta = blockIdx.x;
     const int slice = cta % a.nslices; cta /= a.nslices;
-    const int grp_local = cta % a.ngroups; cta /= a.ngroups;
+    const int set = cta % a.nsets; cta /= a.nsets;
     const int d = cta;
-    const int grp = a.group0 + grp_local;
+    const int grp0 = a.group0 + set * a.gpc;                           // first group of this CTA
+    const int ng = min(a.gpc, a.ngroups_total - grp0);                 // groups this CTA really has (the last set may hold one)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned int* counter = a.barrier + d * a.ngroups_total + grp;
+    unsigned int* counter0 = a.barrier + d * a.ngroups_total + grp0;   // counter of group gi: counter0 + gi
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kLStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         mbar_init(w_full, 1);
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < kLGroups; ++i) mbar_init(&acc_full[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 64);
+        tmem_alloc(tmem_slot, 64 * kLGroups);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -102,33 +108,35 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
             int st = 0, ph = 0;
             long long tm_spin = 0, tm_issue = 0;
             for (int s = 1; s < a.T; ++s) {
-                // wait until every slice of this (direction, group) has published h_{s-1}
-                const unsigned int target = (unsigned int)s * a.nslices;
-                unsigned int spins = 0;
-                const long long c0 = VS_CLK();
-                for (;;) {      // acquire loads: no separate gpu-scope fence (an extra L2 round trip) between the flag and the TMA issue
-                    unsigned int seen;
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-                    if (seen >= target) break;
-                    if (++spins > (1u << 28)) __trap();
-                }
-                const long long c1 = VS_CLK();
-                tm_spin += c1 - c0;
-                asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy flag read -> async-proxy (TMA) data reads
-                const int par = (s - 1) & 1;                       // buffer h_{s-1} was written to
-                const int row0 = ((d * 2 + par) * a.Bp) + grp * kLB;
-                for (int kb = 0; kb < a.nkb; ++kb) {
-                    mbar_wait(&a_empty[st], ph ^ 1);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(&a_full[st], (uint32_t)stage_bytes);
-                        uint8_t* dst = a_ring + (size_t)st * stage_bytes;
-                        tma_load_2d(dst, &tm_h_hi, &a_full[st], kb * 64, row0);
-                        if (nplanes == 2) tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
+                for (int gi = 0; gi < ng; ++gi) {
+                    // wait until every slice of this (direction, group) has published h_{s-1}
+                    const unsigned int target = (unsigned int)s * a.nslices;
+                    unsigned int spins = 0;
+                    const long long c0 = VS_CLK();
+                    for (;;) {      // acquire loads: no separate gpu-scope fence (an extra L2 round trip) between the flag and the TMA issue
+                        unsigned int seen;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter0 + gi) : "memory");
+                        if (seen >= target) break;
+                        if (++spins > (1u << 28)) __trap();
                     }
-                    __syncwarp();
-                    if (++st == kLStages) { st = 0; ph ^= 1; }
+                    const long long c1 = VS_CLK();
+                    tm_spin += c1 - c0;
+                    asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy flag read -> async-proxy (TMA) data reads
+                    const int par = (s - 1) & 1;                       // buffer h_{s-1} was written to
+                    const int row0 = ((d * 2 + par) * a.Bp) + (grp0 + gi) * kLB;
+                    for (int kb = 0; kb < a.nkb; ++kb) {
+                        mbar_wait(&a_empty[st], ph ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&a_full[st], (uint32_t)stage_bytes);
+                            uint8_t* dst = a_ring + (size_t)st * stage_bytes;
+                            tma_load_2d(dst, &tm_h_hi, &a_full[st], kb * 64, row0);
+                            if (nplanes == 2) tma_load_2d(dst + 16384, &tm_h_lo, &a_full[st], kb * 64, row0);
+                        }
+                        __syncwarp();
+                        if (++st == kLStages) { st = 0; ph ^= 1; }
+                    }
+                    tm_issue += VS_CLK() - c1;
                 }
-                tm_issue += VS_CLK() - c1;
             }
             if (TIMING && blockIdx.x == 0 && lane == 0 && a.timing) { a.timing[0] = tm_spin; a.timing[1] = tm_issue; }
         }
@@ -141,8 +149,10 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
             const uint32_t w_addr = smem_u32(w_smem);
             int st = 0, ph = 0;
             long long tm_wait = 0, tm_mma = 0;
-            for (int s = 1; s < a.T; ++s) {
+            for (int s = 1; s < a.T; ++s)
+            for (int gi = 0; gi < ng; ++gi) {
                 uint32_t accumulate = 0;
+                const uint32_t d_t = tmem + (uint32_t)(gi * 64);
                 for (int kb = 0; kb < a.nkb; ++kb) {
                     const long long c0 = VS_CLK();
                     mbar_wait(&a_full[st], ph);
@@ -157,15 +167,15 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (kb * 4 + k < a.nk16) {
-                                umma_bf16(tmem, d_hh + 2 * k, d_wh + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                                umma_bf16(d_t, d_hh + 2 * k, d_wh + 2 * k, idesc, k == 0 ? accumulate : 1u);
                                 if (nplanes == 2) {
-                                    umma_bf16(tmem, d_hl + 2 * k, d_wh + 2 * k, idesc, 1);
-                                    umma_bf16(tmem, d_hh + 2 * k, d_wl + 2 * k, idesc, 1);
+                                    umma_bf16(d_t, d_hl + 2 * k, d_wh + 2 * k, idesc, 1);
+                                    umma_bf16(d_t, d_hh + 2 * k, d_wl + 2 * k, idesc, 1);
                                 }
                             }
                         }
                         umma_commit(&a_empty[st]);
-                        if (kb == a.nkb - 1) umma_commit(acc_full);
+                        if (kb == a.nkb - 1) umma_commit(&acc_full[gi]);
                     }
                     __syncwarp();
                     accumulate = 1;
@@ -177,15 +187,19 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
         }
     } else {
         // ---------------- cell update: thread = one utterance, 16 units ----------------
+        const int gi = (warp - 2) >> 2;                      // which of the CTA's groups this warp belongs to
+        if (gi < ng) {                                       // (the last set may hold a single group: its second cell team has no work)
         const int quad = warp & 3;
-        const int b = grp * kLB + quad * 32 + lane;          // utterance handled by this thread
+        const int b = (grp0 + gi) * kLB + quad * 32 + lane;  // utterance handled by this thread
         const bool valid = b < a.B;
+        unsigned int* counter = counter0 + gi;
+        const bool timed = gi == 0;
         const int u0 = slice * kLU;                          // first hidden unit of the slice
         const int nu = min(kLU, a.H - u0);                   // valid units in this slice
         float c[kLU];
 #pragma unroll
         for (int j = 0; j < kLU; ++j) c[j] = 0.f;
-        const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_base = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gi * 64);
         long long tm_acc = 0, tm_math = 0, tm_store = 0, tm_bar = 0;
         for (int s = 0; s < a.T; ++s) {
             const int t = d ? a.T - 1 - s : s;
@@ -207,7 +221,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
             }
             long long c0 = VS_CLK();
             if (s > 0) {
-                mbar_wait(acc_full, (s - 1) & 1);
+                mbar_wait(&acc_full[gi], (s - 1) & 1);
                 tm_acc += VS_CLK() - c0;
                 c0 = VS_CLK();
                 tc_fence_after();
@@ -275,8 +289,8 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 // publish h_s: the 128 cell threads meet at a CTA barrier, then ONE thread issues the
                 // gpu-scope release (cumulative over the stores ordered before the barrier) and bumps
                 // the counter - the cooperative-groups grid-sync pattern, without a fence per thread
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (threadIdx.x == 64) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + gi) : "memory");
+                if (threadIdx.x == 64 + 128 * gi) {
                     __threadfence();
                     atomicAdd(counter, 1u);
                 }
@@ -306,11 +320,12 @@ __global__ void __launch_bounds__(192, 1) k_lstm_tc(const LstmTcArgs a, const __
                 }
             }
         }
-        if (TIMING && blockIdx.x == 0 && threadIdx.x == 64 && a.timing) { a.timing[4] = tm_acc; a.timing[5] = tm_math; a.timing[6] = tm_store; a.timing[7] = tm_bar; }
+        if (TIMING && timed && blockIdx.x == 0 && threadIdx.x == 64 && a.timing) { a.timing[4] = tm_acc; a.timing[5] = tm_math; a.timing[6] = tm_store; a.timing[7] = tm_bar; }
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 64);
+    if (warp == 1) tmem_dealloc(tmem, 64 * kLGroups);
 }
 
 // W_hh [2][4H][H] fp32 -> [2][nslices*64][Hp] 16-bit hi/lo, row = slice*64 + gate*16 + j
@@ -391,8 +406,14 @@ int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* ho
     const int nplanes = passes == 3 ? 2 : 1;
     const int smem = 1024 + nplanes * a.nkb * 8192 + kLStages * nplanes * 16384 + 256;
     if (smem > s->max_smem) { set_error("lstm_dim too large for the tensor-core recurrent kernel"); return VS_ERR_UNSUPPORTED; }
-    const int max_groups = e->num_sms / (2 * nslices);
-    if (max_groups < 1) { set_error("lstm_dim too large: one step of all slices must be co-resident"); return VS_ERR_UNSUPPORTED; }
+    // CTA sets of `gpc` groups are independent: as many as are co-resident run in one launch (2 directions x nslices CTAs per set).
+    // gpc = 2 (VOICESPLIT_LSTM_GROUPS_PER_CTA=2) interleaves two groups on one CTA; measured at B = 256 (same box, ncu cycles):
+    // 11.53 M cycles against 10.64 M with one group per CTA on twice the SMs - the two chains convoy through the in-order producer /
+    // issuer instead of hiding each other's exchange (profiles/r02_lstm_two_groups_ab.txt) - so one group per CTA stays the default.
+    static const int gpc_env = getenv("VOICESPLIT_LSTM_GROUPS_PER_CTA") ? atoi(getenv("VOICESPLIT_LSTM_GROUPS_PER_CTA")) : 1;
+    a.gpc = (ngroups_total >= 2 && gpc_env >= 2) ? kLGroups : 1;
+    const int max_sets = e->num_sms / (2 * nslices);
+    if (max_sets < 1) { set_error("lstm_dim too large: one step of all slices must be co-resident"); return VS_ERR_UNSUPPORTED; }
     CUtensorMap tm_w_hi, tm_w_lo, tm_h_hi, tm_h_lo;
     {
         uint64_t wd[2] = {(uint64_t)H, (uint64_t)2 * nslices * 64}, ws[1] = {(uint64_t)Hp * sizeof(elt16)};
@@ -412,12 +433,12 @@ int tc_lstm_recurrence(vs_engine* e, void* slot, const float* gates_x, float* ho
                             : (elt ? (const void*)k_lstm_tc<1, false> : (const void*)k_lstm_tc<0, false>);
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return VS_ERR_CUDA; }
-    // groups of 128 utterances are independent: run as many as are co-resident per launch
-    for (int g0 = 0; g0 < ngroups_total; g0 += max_groups) {
-        a.group0 = g0;
-        a.ngroups = ngroups_total - g0 < max_groups ? ngroups_total - g0 : max_groups;
+    const int nsets_total = (ngroups_total + a.gpc - 1) / a.gpc;
+    for (int s0 = 0; s0 < nsets_total; s0 += max_sets) {
+        a.group0 = s0 * a.gpc;
+        a.nsets = nsets_total - s0 < max_sets ? nsets_total - s0 : max_sets;
         void* args[] = {(void*)&a, (void*)&tm_w_hi, (void*)&tm_w_lo, (void*)&tm_h_hi, (void*)&tm_h_lo};
-        ce = cudaLaunchCooperativeKernel(fn, dim3(2 * a.ngroups * nslices), dim3(192), args, (size_t)smem, st);
+        ce = cudaLaunchCooperativeKernel(fn, dim3(2 * a.nsets * nslices), dim3(64 + 128 * a.gpc), args, (size_t)smem, st);
         if (ce != cudaSuccess) { set_error(std::string("k_lstm_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
         e->launches++;
     }
