@@ -147,10 +147,12 @@ __global__ void __launch_bounds__(192, 1) k_lstm_uni_tc(const EncLstmArgs a, con
         for (int s = 1; s < a.S; ++s) {
             const unsigned int target = (unsigned int)s * a.nslices;     // every slice of the group has published h_{s-1}
             unsigned int spins = 0;
-            while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+            for (;;) {      // acquire loads: no separate gpu-scope fence between the flag and the TMA issue (as in k_lstm_tc)
+                unsigned int seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+                if (seen >= target) break;
                 if (++spins > (1u << 28)) __trap();
             }
-            __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy flag read -> async-proxy (TMA) data reads
             const int row0 = ((s - 1) & 1) * a.Np + grp * kEB;
             for (int kb = 0; kb < a.nkb; ++kb) {
@@ -240,10 +242,20 @@ __global__ void __launch_bounds__(192, 1) k_lstm_uni_tc(const EncLstmArgs a, con
                 c[j] = fmaf(fg, c[j], ig * gg);
                 split16<1>(og * tanh_fast(c[j]), vh[j], vl[j]);
             }
-            if (valid) {
+            if (valid) {     // the exchange copy first: only it is on the critical path of the step
                 const size_t xo = ((size_t)(s & 1) * a.Np + n) * a.Hp + u0;
                 *reinterpret_cast<uint4*>(a.hx_hi + xo) = *reinterpret_cast<const uint4*>(vh);
                 *reinterpret_cast<uint4*>(a.hx_lo + xo) = *reinterpret_cast<const uint4*>(vl);
+            }
+            if (s + 1 < a.S) {
+                // publish h_s: CTA barrier of the 128 cell threads, then ONE gpu-scope release + counter bump
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    __threadfence();
+                    atomicAdd(counter, 1u);
+                }
+            }
+            if (valid) {     // the next layer's operand / the projection's input drain behind the release
                 if (a.seq_hi) {
                     const size_t so = ((size_t)n * a.S + s) * a.H + u0;
                     *reinterpret_cast<uint4*>(a.seq_hi + so) = *reinterpret_cast<const uint4*>(vh);
@@ -252,14 +264,6 @@ __global__ void __launch_bounds__(192, 1) k_lstm_uni_tc(const EncLstmArgs a, con
                 if (a.last_hi && s == a.S - 1) {
                     *reinterpret_cast<uint4*>(a.last_hi + (size_t)n * a.H + u0) = *reinterpret_cast<const uint4*>(vh);
                     *reinterpret_cast<uint4*>(a.last_lo + (size_t)n * a.H + u0) = *reinterpret_cast<const uint4*>(vl);
-                }
-            }
-            if (s + 1 < a.S) {
-                // publish h_s: CTA barrier of the 128 cell threads, then ONE gpu-scope release + counter bump
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (threadIdx.x == 64) {
-                    __threadfence();
-                    atomicAdd(counter, 1u);
                 }
             }
         }
