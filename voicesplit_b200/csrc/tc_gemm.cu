@@ -335,19 +335,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmTcArgs a,
                     const int c0 = cgrp * 32 + i * kColStep;
                     if (c0 >= a.n_tile) continue;
                     const int nbase = n0 + c0;
+                    const float bias_l = nbase + lane < a.N ? __ldg(a.bias + nbase + lane) : 0.f;   // one load per chunk, broadcast below
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = nbase + j;
-                        tr[lane * 33 + j] = sigmoid_f(acc[i][j] + (n < a.N ? a.bias[n] : 0.f));
-                    }
+                    for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = sigmoid_f(acc[i][j] + __shfl_sync(0xffffffffu, bias_l, j));
                     __syncwarp();
                     const int n = nbase + lane;
                     if (n < a.N && c0 + lane < a.n_tile) {
-                        for (int r = 0; r < 32 && m0 + r < a.M; ++r) {
-                            const float v = tr[r * 33 + lane];
-                            const size_t o = (size_t)(m0 + r) * a.ld_out + n;
-                            a.out32[o] = v;
-                            if (a.masked) a.masked[o] = a.xmul[o] * v;
+                        if (m0 + 32 <= a.M) {
+                            // the spectrogram values come from HBM: 16 loads in flight per lane before the first use (a rolled loop
+                            // of load -> multiply -> store waited one DRAM latency per row: 47 % of the kernel's samples on that FMUL)
+#pragma unroll
+                            for (int r0 = 0; r0 < 32; r0 += 16) {
+                                float xv[16];
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    xv[k] = a.masked ? __ldg(a.xmul + (size_t)(m0 + r0 + k) * a.ld_out + n) : 0.f;
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    const float v = tr[(r0 + k) * 33 + lane];
+                                    const size_t o = (size_t)(m0 + r0 + k) * a.ld_out + n;
+                                    a.out32[o] = v;
+                                    if (a.masked) a.masked[o] = xv[k] * v;
+                                }
+                            }
+                        } else {
+                            for (int r = 0; r < 32 && m0 + r < a.M; ++r) {
+                                const float v = tr[r * 33 + lane];
+                                const size_t o = (size_t)(m0 + r) * a.ld_out + n;
+                                a.out32[o] = v;
+                                if (a.masked) a.masked[o] = a.xmul[o] * v;
+                            }
                         }
                     }
                     __syncwarp();
