@@ -79,7 +79,9 @@ __device__ __forceinline__ float act_fast(float x) {
     return mish_f(x);
 }
 
-template <int ACT, int ELT, bool OUT32, bool F8C, int EW>
+// GEO = 1: the flat 5x5 fp16_f8c layers (cnn3..7 in eval, 89 % of the FLOPs) get an MMA-issue loop whose schedule is a compile-time
+// constant (see the issuer below); GEO = 0 is the general loop (any geometry / precision / 2-D tiles).
+template <int ACT, int ELT, bool OUT32, bool F8C, int EW, int GEO = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
                                                     const __grid_constant__ CUtensorMap tm_w_hi,
@@ -220,6 +222,73 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
             const uint64_t w_desc0 = make_smem_desc(smem_u32(w_ring), 16, 1024, 2);     // slot 0 of the weight ring / strip ring
             const uint64_t s_desc0 = make_smem_desc(smem_u32(s_ring), 16, 1024, 2);
+            if (GEO == 1) {
+                // Fixed schedule of a 5x5 fp16_f8c tile: 15 steps x (W_hi tile, e4m3 tile) = 30 weight tiles = exactly 6 turns of the
+                // 5-slot weight ring, so slot AND parity of every weight wait are compile-time constants and the ring state is
+                // the same at every tile start; 10 strips per tile walk the 4-slot strip ring ((count + k) & 3).  Fully unrolled:
+                // the issuing warp executes the waits, 8 MMAs and 2 commits per step and nothing else - in the general loop its
+                // ~100 bookkeeping instructions per step (ring wraps, runtime trip counts, constant-bank reloads; single warp,
+                // ~10 cycles each) took as long as the 8 MMAs themselves (ncu source view, r02 final conv capture).
+                constexpr int kSteps = 15;
+                static_assert(kWStages == 5 && (2 * kSteps) % kWStages == 0 && ((2 * kSteps) / kWStages) % 2 == 0, "weight ring schedule");
+                const uint32_t strip_d = (uint32_t)(strip_bytes >> 4);
+                uint32_t scount = 0;                       // strips consumed so far (s_stages == 4, checked by the launcher)
+                int it = 0;
+                for (int itn = 0; itn < a.n_iter; ++itn) {
+                    if (blockIdx.x + itn * gridDim.x >= a.total_tiles) {
+                        // padding iteration: no pixels, but the cluster's shared weight stages must still be consumed and released
+#pragma unroll
+                        for (int t = 0; t < 2 * kSteps; ++t) {
+                            mbar_wait(&w_full[t % kWStages], (t / kWStages) & 1);
+                            if (elect_one()) { if (a.csz > 1) umma_commit_mc(&w_empty[t % kWStages], cmask); else umma_commit(&w_empty[t % kWStages]); }
+                            __syncwarp();
+                        }
+                        continue;
+                    }
+                    const int buf = it & 1, aph = (it >> 1) & 1;
+                    ++it;
+                    mbar_wait(&acc_empty[buf], aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + (uint32_t)(buf * a.N);
+#pragma unroll
+                    for (int dt = 0; dt < 5; ++dt) {
+                        const uint32_t k0 = scount + 2u * dt, k1 = k0 + 1u;
+                        const uint32_t st0 = k0 & 3u, st1 = k1 & 3u;
+                        mbar_wait(&s_full[st0], (k0 >> 2) & 1u);
+                        mbar_wait(&s_full[st1], (k1 >> 2) & 1u);
+                        const uint64_t sd0 = s_desc0 + (uint64_t)(st0 * strip_d), sd1 = s_desc0 + (uint64_t)(st1 * strip_d);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            constexpr int kDummy = 0; (void)kDummy;
+                            const int t0 = 2 * (dt * 3 + j), t1 = t0 + 1;          // constants after unrolling
+                            const uint64_t b0 = sd0 + (uint64_t)(16 * j), b1 = sd1 + (uint64_t)(16 * j);
+                            mbar_wait(&w_full[t0 % kWStages], (t0 / kWStages) & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t a0 = w_desc0 + (uint64_t)((t0 % kWStages) * (kWTileBytes >> 4));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (dt == 0 && j == 0 && k == 0) ? 0u : 1u);
+                                if (a.csz > 1) umma_commit_mc(&w_empty[t0 % kWStages], cmask); else umma_commit(&w_empty[t0 % kWStages]);
+                            }
+                            __syncwarp();
+                            mbar_wait(&w_full[t1 % kWStages], (t1 / kWStages) & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t a1 = w_desc0 + (uint64_t)((t1 % kWStages) * (kWTileBytes >> 4));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_f8(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc8, 1u);
+                                if (a.csz > 1) umma_commit_mc(&w_empty[t1 % kWStages], cmask); else umma_commit(&w_empty[t1 % kWStages]);
+                            }
+                            __syncwarp();
+                        }
+                        if (elect_one()) { umma_commit(&s_empty[st0]); umma_commit(&s_empty[st1]); }
+                        __syncwarp();
+                    }
+                    scount += 10u;
+                    if (elect_one()) umma_commit(&acc_full[buf]);
+                    __syncwarp();
+                }
+            } else {
             int ws = 0, wph = 0, ss = 0, sph = 0, it = 0;
             for (int itn = 0; itn < a.n_iter; ++itn) {
                 if (blockIdx.x + itn * gridDim.x >= a.total_tiles) {
@@ -307,6 +376,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                 }
                 if (elect_one()) umma_commit(&acc_full[buf]);
                 __syncwarp();
+            }
             }
         }
     } else {
@@ -894,6 +964,7 @@ struct TcState {
     elt16* p8_w[2] = {};      // cnn8 on tensor cores: [elt][32 rows (16 hi, 16 lo)][64]
     uint8_t* p8_w8 = nullptr; // its e4m3(2^-8 w_hi) tile [16][64]
     int point8_mma = 1;       // VOICESPLIT_POINT8_MMA = 0 selects the CUDA-core cnn8 kernel
+    int fixed_schedule = 1;   // VOICESPLIT_CONV_FIXED_SCHEDULE = 0: general MMA-issue loop for the 5x5 fp16_f8c layers too
     elt16* wT_hi[2][8] = {};  // training: data-gradient weights (taps flipped, channels transposed), same tile format
     elt16* wT_lo[2][8] = {};
     float* unscale[8] = {};   // 64 copies of 1 / (power-of-two weight scale): epilogue scale of the raw-output convs
@@ -919,6 +990,7 @@ int tc_create(vs_engine* e) {
     if (const char* c = getenv("VOICESPLIT_CONV_TILE2D_DGRAD")) s->tile2d_dgrad = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_L2PREFETCH")) s->l2_prefetch = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_POINT8_MMA")) s->point8_mma = atoi(c) != 0;
+    if (const char* c = getenv("VOICESPLIT_CONV_FIXED_SCHEDULE")) s->fixed_schedule = atoi(c) != 0;
     if (const char* c = getenv("VOICESPLIT_CONV_CLUSTER")) {
         const int v = atoi(c);
         if (v == 1 || v == 2 || v == 4 || v == 8) s->cluster = v;
@@ -1115,21 +1187,22 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     const int ew = a.tile2d ? kEpiWarps2D : kEpiWarpsFlat;
     cfg.blockDim = dim3(conv_threads(ew)); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = a.csz > 1 ? 1 : 0;
-#define VS_CONV_TC_EW(A, E, O, F8, W)                                                                            \
+#define VS_CONV_TC_EW(A, E, O, F8, W) VS_CONV_TC_G(A, E, O, F8, W, 0)
+#define VS_CONV_TC_G(A, E, O, F8, W, G)                                                                          \
     do {                                                                                                         \
-        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+        ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8, W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
         int max_ctas = e->num_sms;                                                                               \
         if (ce == cudaSuccess && a.csz > 1) {                                                                    \
             int ncl = 0;                                                                                         \
             cfg.gridDim = dim3((unsigned)(e->num_sms / a.csz * a.csz));                                          \
-            ce = cudaOccupancyMaxActiveClusters(&ncl, k_conv_tc<A, E, O, F8, W>, &cfg);                           \
+            ce = cudaOccupancyMaxActiveClusters(&ncl, k_conv_tc<A, E, O, F8, W, G>, &cfg);                        \
             if (ce == cudaSuccess && ncl < 1) { set_error("conv clusters do not fit the device"); return VS_ERR_UNSUPPORTED; } \
             max_ctas = ncl * a.csz < e->num_sms ? ncl * a.csz : e->num_sms / a.csz * a.csz;                       \
         }                                                                                                        \
         grid = a.total_tiles < max_ctas ? (a.total_tiles + a.csz - 1) / a.csz * a.csz : max_ctas;                \
         a.n_iter = (a.total_tiles + grid - 1) / grid;                                                            \
         cfg.gridDim = dim3((unsigned)grid);                                                                      \
-        if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_conv_tc<A, E, O, F8, W>, a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
+        if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_conv_tc<A, E, O, F8, W, G>, a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
 #define VS_CONV_TC(A, E, O, F8)                                                                 \
     do { if (a.tile2d) VS_CONV_TC_EW(A, E, O, F8, kEpiWarps2D); else VS_CONV_TC_EW(A, E, O, F8, kEpiWarpsFlat); } while (0)
@@ -1137,10 +1210,16 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
         if (call.act != 2) { set_error("fp32-output conv is pass-through only"); return VS_ERR_INVALID; }
         if (elt) VS_CONV_TC(2, 1, true, false); else VS_CONV_TC(2, 0, true, false);
     } else if (call.f8c) {
-        if (a.act == VS_ACT_RELU) VS_CONV_TC(VS_ACT_RELU, 1, false, true); else VS_CONV_TC(VS_ACT_MISH, 1, false, true);
+        // the flat 5x5 layers take the issuer with the compile-time schedule (VOICESPLIT_CONV_FIXED_SCHEDULE=0: the general loop)
+        const bool fixed_sched = s->fixed_schedule && !a.tile2d && a.n_dt == 5 && a.n_j == 3 && a.s_stages == 4 && a.passes == 3 && a.N == 256;
+        if (fixed_sched) {
+            if (a.act == VS_ACT_RELU) VS_CONV_TC_G(VS_ACT_RELU, 1, false, true, kEpiWarpsFlat, 1);
+            else VS_CONV_TC_G(VS_ACT_MISH, 1, false, true, kEpiWarpsFlat, 1);
+        } else if (a.act == VS_ACT_RELU) VS_CONV_TC(VS_ACT_RELU, 1, false, true); else VS_CONV_TC(VS_ACT_MISH, 1, false, true);
     } else if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1, false, false); else VS_CONV_TC(VS_ACT_RELU, 0, false, false); }
     else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1, false, false); else VS_CONV_TC(VS_ACT_MISH, 0, false, false); }
 #undef VS_CONV_TC_EW
+#undef VS_CONV_TC_G
 #undef VS_CONV_TC
     if (ce == cudaSuccess) ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_error(std::string("k_conv_tc launch: ") + cudaGetErrorString(ce)); return VS_ERR_CUDA; }
