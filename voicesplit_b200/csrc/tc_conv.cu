@@ -79,8 +79,9 @@ __device__ __forceinline__ float act_fast(float x) {
     return mish_f(x);
 }
 
-// GEO = 1: the flat 5x5 fp16_f8c layers (cnn3..7 in eval, 89 % of the FLOPs) get an MMA-issue loop whose schedule is a compile-time
-// constant (see the issuer below); GEO = 0 is the general loop (any geometry / precision / 2-D tiles).
+// GEO = 1 / 2: the flat 5x5 layers in a two-plane mode (fp16_f8c, fp16x3, bf16x3; cnn3..7 = 89 % of the FLOPs, also the training
+// forward and data gradient) get an MMA-issue loop whose schedule is a compile-time constant (see the issuer below), without (1) /
+// with (2) the 2-CTA weight multicast; GEO = 0 is the general loop (any geometry / precision / cluster size / 2-D tiles).
 template <int ACT, int ELT, bool OUT32, bool F8C, int EW, int GEO = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
             const uint64_t w_desc0 = make_smem_desc(smem_u32(w_ring), 16, 1024, 2);     // slot 0 of the weight ring / strip ring
             const uint64_t s_desc0 = make_smem_desc(smem_u32(s_ring), 16, 1024, 2);
-            if (GEO == 1) {
+            if (GEO != 0) {
+                constexpr bool MC = GEO == 2;             // commits are multicast to both CTAs of the cluster
                 // Fixed schedule of a 5x5 fp16_f8c tile: 15 steps x (W_hi tile, e4m3 tile) = 30 weight tiles = exactly 6 turns of the
                 // 5-slot weight ring, so slot AND parity of every weight wait are compile-time constants and the ring state is
                 // the same at every tile start; 10 strips per tile walk the 4-slot strip ring ((count + k) & 3).  Fully unrolled:
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
 #pragma unroll
                         for (int t = 0; t < 2 * kSteps; ++t) {
                             mbar_wait(&w_full[t % kWStages], (t / kWStages) & 1);
-                            if (elect_one()) { if (a.csz > 1) umma_commit_mc(&w_empty[t % kWStages], cmask); else umma_commit(&w_empty[t % kWStages]); }
+                            if (elect_one()) { if (MC) umma_commit_mc(&w_empty[t % kWStages], cmask); else umma_commit(&w_empty[t % kWStages]); }
                             __syncwarp();
                         }
                         continue;
@@ -268,7 +270,11 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                                 const uint64_t a0 = w_desc0 + (uint64_t)((t0 % kWStages) * (kWTileBytes >> 4));
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (dt == 0 && j == 0 && k == 0) ? 0u : 1u);
-                                if (a.csz > 1) umma_commit_mc(&w_empty[t0 % kWStages], cmask); else umma_commit(&w_empty[t0 % kWStages]);
+                                if (!F8C) {                  // split operands: W_hi against both strips (hi*hi + lo*hi)
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
+                                }
+                                if (MC) umma_commit_mc(&w_empty[t0 % kWStages], cmask); else umma_commit(&w_empty[t0 % kWStages]);
                             }
                             __syncwarp();
                             mbar_wait(&w_full[t1 % kWStages], (t1 / kWStages) & 1);
@@ -276,8 +282,11 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
                             if (elect_one()) {
                                 const uint64_t a1 = w_desc0 + (uint64_t)((t1 % kWStages) * (kWTileBytes >> 4));
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f8(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc8, 1u);
-                                if (a.csz > 1) umma_commit_mc(&w_empty[t1 % kWStages], cmask); else umma_commit(&w_empty[t1 % kWStages]);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (F8C) umma_f8(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc8, 1u);      // e4m3 correction tile x c8 strip
+                                    else umma_bf16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1u);         // hi*lo: W_lo x S_hi
+                                }
+                                if (MC) umma_commit_mc(&w_empty[t1 % kWStages], cmask); else umma_commit(&w_empty[t1 % kWStages]);
                             }
                             __syncwarp();
                         }
@@ -1187,7 +1196,6 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
     const int ew = a.tile2d ? kEpiWarps2D : kEpiWarpsFlat;
     cfg.blockDim = dim3(conv_threads(ew)); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = a.csz > 1 ? 1 : 0;
-#define VS_CONV_TC_EW(A, E, O, F8, W) VS_CONV_TC_G(A, E, O, F8, W, 0)
 #define VS_CONV_TC_G(A, E, O, F8, W, G)                                                                          \
     do {                                                                                                         \
         ce = cudaFuncSetAttribute(k_conv_tc<A, E, O, F8, W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
@@ -1204,21 +1212,23 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
         cfg.gridDim = dim3((unsigned)grid);                                                                      \
         if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&cfg, k_conv_tc<A, E, O, F8, W, G>, a, tm_in_hi, tm_in_lo, tm_w_hi, tm_w_lo); \
     } while (0)
+    // the flat 5x5 layers in a two-plane mode take the issuer with the compile-time schedule (VOICESPLIT_CONV_FIXED_SCHEDULE=0: general loop)
+    const int geo = (s->fixed_schedule && !a.tile2d && a.n_dt == 5 && a.n_j == 3 && a.s_stages == 4 && a.passes == 3 && a.N == 256 &&
+                     (a.csz == 1 || a.csz == 2)) ? a.csz : 0;
 #define VS_CONV_TC(A, E, O, F8)                                                                 \
-    do { if (a.tile2d) VS_CONV_TC_EW(A, E, O, F8, kEpiWarps2D); else VS_CONV_TC_EW(A, E, O, F8, kEpiWarpsFlat); } while (0)
+    do {                                                                                        \
+        if (a.tile2d) VS_CONV_TC_G(A, E, O, F8, kEpiWarps2D, 0);                                \
+        else if (geo == 1) VS_CONV_TC_G(A, E, O, F8, kEpiWarpsFlat, 1);                         \
+        else if (geo == 2) VS_CONV_TC_G(A, E, O, F8, kEpiWarpsFlat, 2);                         \
+        else VS_CONV_TC_G(A, E, O, F8, kEpiWarpsFlat, 0);                                       \
+    } while (0)
     if (call.out32) {
         if (call.act != 2) { set_error("fp32-output conv is pass-through only"); return VS_ERR_INVALID; }
         if (elt) VS_CONV_TC(2, 1, true, false); else VS_CONV_TC(2, 0, true, false);
     } else if (call.f8c) {
-        // the flat 5x5 layers take the issuer with the compile-time schedule (VOICESPLIT_CONV_FIXED_SCHEDULE=0: the general loop)
-        const bool fixed_sched = s->fixed_schedule && !a.tile2d && a.n_dt == 5 && a.n_j == 3 && a.s_stages == 4 && a.passes == 3 && a.N == 256;
-        if (fixed_sched) {
-            if (a.act == VS_ACT_RELU) VS_CONV_TC_G(VS_ACT_RELU, 1, false, true, kEpiWarpsFlat, 1);
-            else VS_CONV_TC_G(VS_ACT_MISH, 1, false, true, kEpiWarpsFlat, 1);
-        } else if (a.act == VS_ACT_RELU) VS_CONV_TC(VS_ACT_RELU, 1, false, true); else VS_CONV_TC(VS_ACT_MISH, 1, false, true);
+        if (a.act == VS_ACT_RELU) VS_CONV_TC(VS_ACT_RELU, 1, false, true); else VS_CONV_TC(VS_ACT_MISH, 1, false, true);
     } else if (a.act == VS_ACT_RELU) { if (elt) VS_CONV_TC(VS_ACT_RELU, 1, false, false); else VS_CONV_TC(VS_ACT_RELU, 0, false, false); }
     else { if (elt) VS_CONV_TC(VS_ACT_MISH, 1, false, false); else VS_CONV_TC(VS_ACT_MISH, 0, false, false); }
-#undef VS_CONV_TC_EW
 #undef VS_CONV_TC_G
 #undef VS_CONV_TC
     if (ce == cudaSuccess) ce = cudaGetLastError();
