@@ -41,9 +41,12 @@ using namespace ptx;
 
 constexpr int kWStages = 5;             // weight tiles (16 KB each) in flight
 // Epilogue warps: 4 per TMEM lane quadrant for the flat tiles (N = 256: 8 chunks of 32 columns, two per warp).  The 2-D tiles of
-// cnn2 (N = 224: 7 chunks) have less than half the MMA work per tile (7 single-tap steps), so the epilogue sets their pace:
-// they run 7 warps per quadrant, one chunk each (960 threads, <= 64 registers).
-constexpr int kEpiWarpsFlat = 16, kEpiWarps2D = 28;
+// cnn2 (N = 224: 7 chunks, 4 paired steps) have a quarter of the MMA work per tile, so the epilogue sets their pace; a same-box
+// sweep of 8 / 12 / 16 / 20 / 28 warps gave 10.65 / 10.87 / 10.15 / 10.65 / 10.92 M cycles per launch: 16 (<= 113 registers) it is.
+#ifndef VS_EPI_WARPS_2D
+#define VS_EPI_WARPS_2D 16
+#endif
+constexpr int kEpiWarpsFlat = 16, kEpiWarps2D = VS_EPI_WARPS_2D;
 constexpr int conv_threads(int ew) { return 64 + 32 * ew; }
 constexpr int kWTileBytes = 128 * 128;  // 128 rows x 64 bf16
 
@@ -81,7 +84,8 @@ __device__ __forceinline__ float act_fast(float x) {
 
 // GEO = 1 / 2: the flat 5x5 layers in a two-plane mode (fp16_f8c, fp16x3, bf16x3; cnn3..7 = 89 % of the FLOPs, also the training
 // forward and data gradient) get an MMA-issue loop whose schedule is a compile-time constant (see the issuer below), without (1) /
-// with (2) the 2-CTA weight multicast; GEO = 0 is the general loop (any geometry / precision / cluster size / 2-D tiles).
+// with (2) the 2-CTA weight multicast; GEO = 0 is the general loop (any geometry / precision / cluster size); GEO = 3: 2-D tiles
+// (general loop, the epilogue pairs taps along T).
 template <int ACT, int ELT, bool OUT32, bool F8C, int EW, int GEO = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArgs a, const __grid_constant__ CUtensorMap tm_in_hi,
                                                     const __grid_constant__ CUtensorMap tm_in_lo,
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
             const uint64_t w_desc0 = make_smem_desc(smem_u32(w_ring), 16, 1024, 2);     // slot 0 of the weight ring / strip ring
             const uint64_t s_desc0 = make_smem_desc(smem_u32(s_ring), 16, 1024, 2);
-            if (GEO != 0) {
+            if (GEO == 1 || GEO == 2) {
                 constexpr bool MC = GEO == 2;             // commits are multicast to both CTAs of the cluster
                 // Fixed schedule of a 5x5 fp16_f8c tile: 15 steps x (W_hi tile, e4m3 tile) = 30 weight tiles = exactly 6 turns of the
                 // 5-slot weight ring, so slot AND parity of every weight wait are compile-time constants and the ring state is
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
         // sub-partition against 6.3 k cycles of MMA), so it is kept branch-free and short: interior chunks (no row padding, no
         // tile / plane edge: the common case) take a path without per-pixel bookkeeping, store addresses are one base pointer per
         // chunk plus compile-time offsets, the activation is nine straight-line instructions (common.cuh: mish_f).
-        constexpr bool T2D = (EW == kEpiWarps2D);        // the launch pairs the 2-D tiles with this warp count
+        constexpr bool T2D = (GEO == 3);                 // 2-D tiles (the 7x1 layer with taps paired along T)
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
         const int cgrp = (warp - 2) >> 2;                // which 32-column chunks this warp takes
         const int co = quad * 16 + (lane >> 1), h = lane & 1;
@@ -1217,7 +1221,7 @@ static int launch_conv_tc_ex(vs_engine* e, int layer, const elt16* in_hi, const 
                      (a.csz == 1 || a.csz == 2)) ? a.csz : 0;
 #define VS_CONV_TC(A, E, O, F8)                                                                 \
     do {                                                                                        \
-        if (a.tile2d) VS_CONV_TC_G(A, E, O, F8, kEpiWarps2D, 0);                                \
+        if (a.tile2d) VS_CONV_TC_G(A, E, O, F8, kEpiWarps2D, 3);                                \
         else if (geo == 1) VS_CONV_TC_G(A, E, O, F8, kEpiWarpsFlat, 1);                         \
         else if (geo == 2) VS_CONV_TC_G(A, E, O, F8, kEpiWarpsFlat, 2);                         \
         else VS_CONV_TC_G(A, E, O, F8, kEpiWarpsFlat, 0);                                       \
