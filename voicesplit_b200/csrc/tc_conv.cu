@@ -137,7 +137,62 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
     if (warp == 0) {
         // ===================== TMA producer =====================
         // whole warp: warp-uniform loops and barrier waits; one elected lane arms the barrier and issues the TMA loads
-        {
+        if (GEO == 1 || GEO == 2) {
+            // Fixed schedule of the flat 5x5 two-plane layers (see the MMA issuer): slot and parity of every weight-ring wait are
+            // compile-time constants, the 10 strips of a tile walk the 4-slot strip ring.  The general loop below kept this warp
+            // busy ~75 % of the time with ring / trip-count bookkeeping - barely ahead of the tensor pipe, so the weight ring was
+            // rarely full when the issuer needed it.
+            constexpr bool MC = GEO == 2;
+            constexpr int kSliceRows = MC ? 64 : 128;
+            const int w_row0 = MC ? (int)crank * kSliceRows : 0;
+            uint8_t* const w_dst0 = w_ring + (size_t)w_row0 * 128;
+            uint32_t scount = 0;
+            for (int itn = 0; itn < a.n_iter; ++itn) {
+                const int tile = blockIdx.x + itn * gridDim.x;
+                const bool valid = tile < a.total_tiles;    // a padding iteration still takes part in the shared weight stream
+                const int b = valid ? tile / a.tiles_per_utt : 0;
+                const int q0 = (tile - b * a.tiles_per_utt) * useful;
+#pragma unroll
+                for (int dt = 0; dt < 5; ++dt) {
+                    if (valid) {
+                        const int qs = q0 - a.halo + (dt - 2) * a.dt_stride;
+#pragma unroll
+                        for (int sp = 0; sp < 2; ++sp) {
+                            const uint32_t k = scount + 2u * dt + sp, st = k & 3u;
+                            mbar_wait(&s_empty[st], ((k >> 2) & 1u) ^ 1u);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&s_full[st], (uint32_t)strip_bytes);
+                                uint8_t* dst = s_ring + (size_t)st * strip_bytes;
+                                for (int i = 0; i < a.n_boxes; ++i)
+                                    tma_load_3d(dst + (size_t)i * a.box_rows * 128, sp == 0 ? &tm_in_hi : &tm_in_lo, &s_full[st], 0,
+                                                qs + i * a.box_rows, b);
+                            }
+                            __syncwarp();
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                        for (int wp = 0; wp < 2; ++wp) {
+                            const int t = 2 * (dt * 3 + j) + wp;                   // constants after unrolling
+                            mbar_wait(&w_empty[t % kWStages], ((t / kWStages) & 1) ^ 1);    // released by the MMA threads of all cluster members
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&w_full[t % kWStages], kWTileBytes);
+                                const void* tm = wp == 0 ? (const void*)&tm_w_hi : (const void*)&tm_w_lo;
+                                if (MC) tma_load_2d_mc(w_dst0 + (size_t)(t % kWStages) * kWTileBytes, tm, &w_full[t % kWStages], 0,
+                                                       (dt * 3 + j) * 128 + w_row0, cmask);
+                                else tma_load_2d(w_dst0 + (size_t)(t % kWStages) * kWTileBytes, tm, &w_full[t % kWStages], 0, (dt * 3 + j) * 128);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+                if (valid) scount += 10u;
+            }
+            // drain: every arrival peers still owe this CTA's w_empty barriers has landed before the CTA may exit
+            if (MC)
+                for (int i = 0; i < kWStages; ++i) mbar_wait(&w_empty[i], 1);
+        } else {
             int ws = 0, wph = 0, ss = 0, sph = 0;
             const int slice_rows = 128 / a.csz;
             for (int itn = 0; itn < a.n_iter; ++itn) {
