@@ -200,6 +200,35 @@ def _several_groups_body(B):
             assert torch.allclose(full[b:b + 1], one, atol=2e-6, rtol=0), (precision, b)
 
 
+def _gemm_pairs_body():
+    """LSTM input projection, FC1 and FC2 through the W-tile multicast pairs (2-CTA clusters) on a problem with an odd number of
+    M blocks (the last pair has a CTA without rows) and N tails - against the fp32 path."""
+    dims = synth.make_dims(65, 32, 48, 64)
+    sd = synth.make_state_dict(dims, 5, "stress")
+    eng = MaskEngine(activation="mish", **dims)
+    eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
+    x, emb = synth.make_inputs(5, 77, dims, 3)            # 385 rows = 3 full M blocks + 1 row
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
+    ref, ref_m = eng.forward(xt, et, precision="fp32", want_masked=True)
+    for precision in ("fp16x3", "bf16x3", "fp16_f8c"):
+        out, out_m = eng.forward(xt, et, precision=precision, want_masked=True)
+        torch.cuda.synchronize()
+        assert (out - ref).abs().max() < TOL_MAX[precision], precision
+        assert (out_m - ref_m).abs().max() < TOL_MAX[precision], precision
+
+
+def test_gemm_weight_tile_multicast_pairs_on_a_small_problem():
+    """The pairs are normally enabled only for GEMMs with at least two waves of tiles (the full-size input projection, covered by
+    bench.py's parity block); VOICESPLIT_GEMM_CLUSTER=3 forces them wherever there are two M blocks.  Read once per process ->
+    child process."""
+    import subprocess, sys, os
+    env = dict(os.environ, VOICESPLIT_GEMM_CLUSTER="3")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; t._gemm_pairs_body()"
+            % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_abi_error_paths():
     """Errors surface as codes + messages, never as silent fallbacks."""
     import ctypes

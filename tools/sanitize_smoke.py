@@ -1,5 +1,6 @@
 """Small end-to-end run for compute-sanitizer: eval forward in every precision, training step, audio round trip."""
 import os, sys
+os.environ.setdefault("VOICESPLIT_GEMM_CLUSTER", "3")     # small problems take the W-tile multicast pairs too
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from voicesplit_b200 import config, synth
@@ -10,7 +11,7 @@ dims = synth.make_dims(33, 16, 24, 40)
 sd = synth.make_state_dict(dims, 2, "stress")
 eng = MaskEngine(activation="mish", **dims)
 eng.load_state_dict_tensors({k: torch.from_numpy(v).cuda() for k, v in sd.items() if "num_batches" not in k})
-x, emb = synth.make_inputs(3, 37, dims, 12)
+x, emb = synth.make_inputs(5, 53, dims, 12)      # 265 rows: three M blocks, the last pair has an empty CTA
 xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(emb).cuda()
 ref = eng.forward(xt, et, precision="fp32")
 for p in ("fp16x3", "fp16_f8c", "bf16x3", "fp16", "bf16"):

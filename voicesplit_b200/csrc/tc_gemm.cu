@@ -513,7 +513,8 @@ int launch_gemm_tc(vs_engine* e, int epi, int kid, const elt16* a_hi, const elt1
     a.total_tiles = a.n_tiles_m * a.n_tiles_n;
     a.n_kb = (a.K + 63) / 64;
     // pairs of M blocks share their W tiles through TMA multicast when there is enough work for every cluster (the large GEMMs)
-    a.csz = (g->cluster > 1 && !a.tn && a.n_tile % 16 == 0 && a.total_tiles >= 2 * e->num_sms) ? 2 : 1;
+    // (cluster == 3, VOICESPLIT_GEMM_CLUSTER=3: pairs whenever there are two M blocks - lets small test problems take this path)
+    a.csz = (g->cluster > 1 && !a.tn && a.n_tile % 16 == 0 && (g->cluster == 3 ? a.n_tiles_m >= 2 : a.total_tiles >= 2 * e->num_sms)) ? 2 : 1;
     if (a.lda % 8 || a.ldw % 8) { set_error("tensor-core GEMM needs 16-byte aligned operand rows (lstm_dim % 4 == 0)"); return VS_ERR_INVALID; }
     CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
     {
@@ -693,7 +694,7 @@ static GemmState* g_state(vs_engine* e) {
     if (!hdr->gemm) {
         GemmState* g = new GemmState();
         cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
-        if (const char* c = getenv("VOICESPLIT_GEMM_CLUSTER")) g->cluster = atoi(c) == 1 ? 1 : 2;
+        if (const char* c = getenv("VOICESPLIT_GEMM_CLUSTER")) g->cluster = atoi(c) == 1 ? 1 : (atoi(c) == 3 ? 3 : 2);
         hdr->gemm = g;
     }
     return (GemmState*)hdr->gemm;
