@@ -375,7 +375,8 @@ def main():
                          "recurrence": {"ms": rc_ms, "achieved": a_rc, "frac": a_rc / peak, "us_per_step": rc_ms * 1e3 / T,
                                         "note": "T sequential steps; bounded by the per-step exchange latency, not by the tensor pipe"},
                          "algorithmic_flops_per_launch": fl["lstm"] * B,
-                         "ncu_tensor_pipe_pct": "profiles/r02_ncu_lstm_summary.txt / r01_ncu_gemm_summary.txt"}
+                         "ncu_tensor_pipe_pct": {"input_projection": 67.7, "recurrence": 13.8,
+                                                 "source": "profiles/r02_ncu_final_gates_f8c_b256_summary.txt, r02_ncu_final_lstm_f8c_b256_summary.txt (ncu --set full at B = 256)"}}
         line = {"metric": METRIC, "value": value, "unit": "utterances/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
