@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
         // The WHOLE warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues the tcgen05
         // instructions.  Keeping the warp converged matters: tcgen05.mma / commit take their operands from uniform registers,
         // and inside an `if (lane == 0)` region the compiler wraps every one of them in an elect-and-loop sequence that costs
-        // ~100 cycles per MMA - as much as the MMA itself (ncu source view, profiles/r02_ncu_conv_f8c_b256_summary.txt).
+        // ~100 cycles per MMA - as much as the MMA itself (ncu source view, profiles/r02_ncu_conv_f8c_b256_before_elect_summary.txt).
         {
             const uint32_t idesc = make_idesc_bf16(128, a.N, ELT);
             const uint32_t idesc8 = make_idesc_e4m3(128, a.N);
@@ -449,10 +449,12 @@ __global__ void __launch_bounds__(conv_threads(EW), 1) k_conv_tc(const ConvTcArg
         }
     } else {
         // ===================== epilogue (warps 2 ..) =====================
-        // The instruction stream of these warps is what bounds the light layers (cnn2: ~8.5 k issue cycles per tile and SM
-        // sub-partition against 6.3 k cycles of MMA), so it is kept branch-free and short: interior chunks (no row padding, no
-        // tile / plane edge: the common case) take a path without per-pixel bookkeeping, store addresses are one base pointer per
-        // chunk plus compile-time offsets, the activation is nine straight-line instructions (common.cuh: mish_f).
+        // The instruction stream of these warps is what bounds the light layer (cnn2 on 2-D tiles: ~7.7 k cycles per tile against
+        // 3.6 k cycles of MMA; ncu: issue + MIO bound, profiles/r02_ncu_final_cnn2_f8c_b256_summary.txt), so it is kept branch-free and
+        // short: interior chunks (no row padding, no tile / plane edge: the common case) and the cut last chunk take paths without
+        // per-pixel bookkeeping, store addresses are one base pointer per chunk plus compile-time offsets, tile coordinates advance
+        // without divisions, the activation is nine straight-line instructions (common.cuh: mish_f), each lane converts and stores
+        // a channel PAIR (one pack instruction per plane).
         constexpr bool T2D = (GEO == 3);                 // 2-D tiles (the 7x1 layer with taps paired along T)
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
         const int cgrp = (warp - 2) >> 2;                // which 32-column chunks this warp takes
