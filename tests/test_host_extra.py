@@ -83,3 +83,26 @@ def test_public_header_is_plain_c_and_cxx():
             continue
         r = subprocess.run(args + [hdr], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm: the reference's CPU path, oracle/torch_port.py) prints ONE JSON line
+    with the keys of the bench contract; run at a tiny shape so that it takes seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--frames", "41", "--freq", "33"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "utterances/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["config"]["frames"] == 41 and d["config"]["freq_bins"] == 33
