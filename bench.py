@@ -141,8 +141,13 @@ def cpu_reference_throughput(dims, T, runs=5, warmup=1, batches=(1, 8), seconds_
     x1, e1 = synth.make_inputs(1, T, dims, 99)
     x1, e1 = torch.from_numpy(x1), torch.from_numpy(e1)
     t_start = time.perf_counter()
-    sweep = {}
-    for nt in sorted({cores, max(1, cores // 2), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+    # ascending, and stopped once a count is clearly past the knee: on the 128-core B200 hosts the all-cores probe takes
+    # ~50 s per forward (oneDNN oversubscription, profiles/r02_bench_default_full.json) against 0.7 s at 8-32 threads
+    sweep, skipped = {}, []
+    for nt in sorted({cores, max(1, cores // 2), min(cores, 32), min(cores, 16), min(cores, 8)}):
+        if sweep and sweep[max(sweep)] > 1.5 * min(sweep.values()):
+            skipped.append(nt)
+            continue
         torch.set_num_threads(nt)
         torch_port.forward(sd, x1, e1)
         t0 = time.perf_counter()
@@ -168,6 +173,7 @@ def cpu_reference_throughput(dims, T, runs=5, warmup=1, batches=(1, 8), seconds_
     return dict(value=per_batch[best_b]["utt_per_s"], unit="utterances/s", cores=best_t, kind="port",
                 host=f"{cpu_model_name()}, {cores} usable cores",
                 per_batch={str(b): v for b, v in per_batch.items()}, thread_sweep_s={str(k): round(v, 4) for k, v in sweep.items()},
+                thread_sweep_skipped=skipped,
                 sample=f"B = {', '.join(str(b) for b in batches)} utterance(s) of {T}x{dims['num_freq']} through oracle/torch_port.py (the reference's own "
                        f"torch.nn CPU ops, fp32, eval), median of {per_batch[best_b]['runs']} runs after warm-up, {best_t} of {cores} host "
                        f"threads (best of a sweep at the full T); value = B = {best_b}"), per_batch[best_b]["median_s"]
