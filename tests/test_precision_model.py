@@ -17,8 +17,8 @@ pm = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(pm)
 
 # (max |diff|, mean |diff|) of the GPU suite for the mode the scheme models.  One exception: the worst bin of fp16_f8c on
-# case tiny_mish_stress is 3.36e-3 in this model (everything but the six emulated conv layers exact) and just under the 3e-3 the GPU
-# suite asserts on the device (whose fp32 stages round differently): one bin in the steep part of the sigmoid (mask 0.563; the next-worst bin is 2.4e-3) sits AT that bound, the MAE
+# case tiny_mish_stress is 3.36e-3 in this model (everything but the six emulated conv layers exact) and 2.69e-3 on the device (profiles/r02_parity_margins.txt; its
+# fp32 stages round differently), against the 3e-3 the GPU suite asserts: one bin in the steep part of the sigmoid (mask 0.563; the next-worst bin is 2.4e-3) sits AT that bound, the MAE
 # (the quantity BASELINE.json's bar is stated on) is 4.8e-5.  The model is held to 5e-3 on the max for that mode.
 BOUNDS = {"fp16x3": (1e-3, 1e-4), "fp16+f8x2_device": (5e-3, 2e-4), "bf16x3": (3e-3, 1e-4)}
 SMALL_MISH = [p for p in golden_cases() if "_mish_" in p and any(t in p for t in ("tiny", "odd", "t1"))]
