@@ -543,7 +543,7 @@ def train_config4(dev, dist, rank, world, want_batch, barrier, steps=3, warmup=2
     e1.record()
     torch.cuda.synchronize()
     local_ms = e0.elapsed_time(e1)
-    loss_val = float(loss)
+    loss_val = float(loss.detach())
     ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events]))
     barrier()
     value, ms = vdist.aggregate_throughput(B * steps, local_ms, dist, dev)

@@ -70,6 +70,6 @@ def test_loss_oracle_against_the_live_reference_on_a_fresh_case():
     loss = gu.SiSNR_With_Pit()(out[:, None, :], ref[:, None, :], torch.from_numpy(lens))
     loss.backward()
     r = loss_oracle.loss_and_grad(est, tgt, phase, lens, n_fft, hop, win, mode="q1")
-    assert abs(r["loss"] - float(loss)) <= 2e-4
+    assert abs(r["loss"] - float(loss.detach())) <= 2e-4
     gs = float(e.grad.abs().max())
     assert np.abs(r["grad_est"] - e.grad.numpy()).max() <= 2e-4 * gs
