@@ -106,3 +106,92 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["config"]["frames"] == 41 and d["config"]["freq_bins"] == 33
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no C compiler")
+def test_ctypes_structs_and_constants_match_the_public_header(tmp_path):
+    """The Python binding (voicesplit_b200/_cabi.py) restates the header's structs and enum values by hand: a C probe compiled
+    against include/voicesplit_b200.h prints sizeof / offsetof of every field and the VS_* constants, which must equal what
+    ctypes lays out - a silent drift here would hand the library mis-aligned pointers."""
+    import ctypes
+    from voicesplit_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"vs_dims": _cabi.VsDims, "vs_params": _cabi.VsParams, "vs_train_state": _cabi.VsTrainState, "vs_grads": _cabi.VsGrads,
+               "vs_audio_params": _cabi.VsAudioParams, "vs_loss_params": _cabi.VsLossParams, "vs_encoder_dims": _cabi.VsEncoderDims,
+               "vs_encoder_params": _cabi.VsEncoderParams}
+    consts = {"VS_OK": _cabi.VS_OK, "VS_ACT_MISH": _cabi.ACT_MISH, "VS_ACT_RELU": _cabi.ACT_RELU,
+              "VS_ISTFT_Q1": 0, "VS_ISTFT_CORRECTED": 1,
+              **{"VS_PREC_" + k.upper(): v for k, v in _cabi.PRECISIONS.items()}}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "voicesplit_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    for k in consts:
+        lines.append(f'  printf("{k} %d\\n", (int)({k}));')
+    lines += ['  return 0;', '}']
+    src, exe = tmp_path / "probe.c", tmp_path / "probe"
+    src.write_text("\n".join(lines))
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+    for k, v in consts.items():
+        assert int(got[k]) == v, k
+    # the engine's string -> enum tables are the same numbers
+    from voicesplit_b200.engine import MaskEngine
+    assert MaskEngine.PHASE_MODES == {"q1": int(got["VS_ISTFT_Q1"]), "corrected": int(got["VS_ISTFT_CORRECTED"])}
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="no C++ compiler")
+def test_ctypes_signatures_match_the_header_prototypes(tmp_path):
+    """Arity and argument class (pointer / 32-bit int / 64-bit int / float / double) of every prototype in the public header, taken
+    from the C++ type system, against the argtypes / restype voicesplit_b200/_cabi.py binds."""
+    import ctypes
+    from voicesplit_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = r'''
+#include <cstdio>
+#include <type_traits>
+#include "voicesplit_b200.h"
+template <class T> constexpr char cls() {
+    return std::is_pointer<T>::value ? 'p' : std::is_same<T, float>::value ? 'f' : std::is_same<T, double>::value ? 'd'
+           : (std::is_integral<T>::value && sizeof(T) == 4) ? 'i' : (std::is_integral<T>::value && sizeof(T) == 8) ? 'l' : '?';
+}
+template <class F> struct Sig;
+template <class R, class... A> struct Sig<R (*)(A...)> {      // decltype(&fn) is unevaluated: nothing to link against
+    static void show(const char* name) {
+        const char s[] = {cls<A>()..., 0};
+        std::printf("%s %c %s\n", name, cls<R>(), s);
+    }
+};
+int main() {
+%s
+    return 0;
+}
+'''
+    body = "\n".join(f'    Sig<decltype(&{n})>::show("{n}");' for n in _cabi.SIGNATURES)
+    src, exe = tmp_path / "sig.cpp", tmp_path / "sig"
+    src.write_text(probe.replace("%s\n    return 0;", body + "\n    return 0;"))
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = {}
+    for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines():
+        parts = line.split(" ")
+        got[parts[0]] = (parts[1], parts[2] if len(parts) > 2 else "")
+
+    def c(t):
+        if t is None:
+            return "v"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._CFuncPtr):
+            return "p"
+        if t is ctypes.c_float:
+            return "f"
+        if t is ctypes.c_double:
+            return "d"
+        return "i" if ctypes.sizeof(t) == 4 else "l"
+    for name, (res, args) in _cabi.SIGNATURES.items():
+        assert got[name] == (c(res), "".join(c(a) for a in args)), (name, got[name])
