@@ -195,3 +195,38 @@ int main() {
         return "i" if ctypes.sizeof(t) == 4 else "l"
     for name, (res, args) in _cabi.SIGNATURES.items():
         assert got[name] == (c(res), "".join(c(a) for a in args)), (name, got[name])
+
+
+def test_every_entry_point_rejects_a_null_engine_without_crashing():
+    """'integer status return, no exceptions across the boundary' (SURVEY 8b): each entry point called with a NULL engine and NULL
+    buffers answers with an error code (size queries with 0) - on a host without a GPU too."""
+    import ctypes
+    from voicesplit_b200 import _cabi
+    lib = _cabi.load()
+    N = ctypes.c_void_p(0)
+    no_sync, no_hook = ctypes.cast(None, _cabi.STAT_ALLREDUCE_FN), ctypes.cast(None, _cabi.BACKWARD_HOOK_FN)
+    failing = [
+        lambda: lib.vs_engine_load_params(N, None, N), lambda: lib.vs_forward(N, N, N, N, N, 1, 1, 0, N, 0, N),
+        lambda: lib.vs_forward_host(N, N, N, N, N, 1, 1, 0, N), lambda: lib.vs_forward_host_submit(N, 0, N, N, N, N, 1, 1, 0),
+        lambda: lib.vs_forward_host_wait(N, 0), lambda: lib.vs_forward_host_reserve(N, 1, 1, 0),
+        lambda: lib.vs_conv_stack(N, N, N, 1, 1, 0, N, 0, N),
+        lambda: lib.vs_train_forward(N, None, N, N, N, 1, 1, N, 0, N), lambda: lib.vs_train_backward(N, N, N, N, N, None, N, N, 1, 1, N, 0, N),
+        lambda: lib.vs_engine_set_train_tensor_cores(N, 1), lambda: lib.vs_engine_set_sync_bn(N, no_sync, N, 1),
+        lambda: lib.vs_engine_set_backward_hook(N, no_hook, N),
+        lambda: lib.vs_audio_configure(N, None, N), lambda: lib.vs_wav2spec(N, N, N, N, 1, 1, N, 0, N), lambda: lib.vs_spec2wav(N, N, N, N, 1, 2, N, 0, N),
+        lambda: lib.vs_loss_configure(N, None, N), lambda: lib.vs_loss_spec2wav(N, N, N, N, 1, 2, N, 0, N),
+        lambda: lib.vs_loss_spec2wav_backward(N, N, N, N, N, 1, 2, N, 0, N), lambda: lib.vs_sisnr_loss(N, N, N, N, N, N, N, N, 1, 2, N, 0, N),
+        lambda: lib.vs_sisnr_wav(N, N, N, N, N, N, 1, 1, N), lambda: lib.vs_sdr(N, N, N, N, 1, 1, N, 0, N),
+        lambda: lib.vs_encoder_configure(N, None, N), lambda: lib.vs_encoder_load_params(N, None, N),
+        lambda: lib.vs_encoder_mel(N, N, N, 1, 1, N, 0, N), lambda: lib.vs_encoder_forward(N, N, N, 1, 1, N, 0, N),
+        lambda: lib.vs_encoder_dvector(N, N, N, 1, 1, N, 0, N),
+        lambda: lib.vs_engine_set_profiling(N, 1), lambda: lib.vs_debug_conv_layer(N, 0, N, N, 1, 1, 0, N),
+        lambda: lib.vs_debug_lstm_head(N, N, N, N, N, N, 1, 1, 0, N), lambda: lib.vs_debug_lstm_timing(N, None),
+    ]
+    for i, call in enumerate(failing):
+        assert call() < 0, i
+    assert lib.vs_last_error()
+    for size in (lib.vs_workspace_bytes(N, 1, 1, 0), lib.vs_train_workspace_bytes(N, 1, 1), lib.vs_audio_workspace_bytes(N, 1, 1),
+                 lib.vs_loss_workspace_bytes(N, 1, 2), lib.vs_encoder_workspace_bytes(N, 1, 1, 1)):
+        assert size == 0
+    assert lib.vs_engine_destroy(N) == 0 and lib.vs_last_launch_count(N) == 0 and lib.vs_profile_read(N, 0, None, None) == 0
