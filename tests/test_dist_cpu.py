@@ -136,3 +136,25 @@ def test_flat_buffer_fast_path_reduces_in_place(overlap):
         assert p.exitcode == 0
     assert n == 10 and aliased and pending
     assert torch.allclose(torch.tensor(flat), torch.arange(10, dtype=torch.float32) * 1.5)     # mean of (1x, 2x), every element exactly once
+
+
+@pytest.mark.parametrize("C", [2, 3])
+def test_general_pit_matches_the_live_reference_with_gradients(C):
+    """C > 1 sources (the permutation search the reference carries but its training never uses, generic_utils.py:443-474): loss and
+    d(loss)/d(estimate) of losses.si_snr_with_pit against the unmodified SiSNR_With_Pit (build container only)."""
+    from oracle import ref_import
+    from voicesplit_b200.losses import si_snr_with_pit
+    if not ref_import.available():
+        pytest.skip("reference tree only exists in the build container")
+    _, _, gu = ref_import.load()
+    g = torch.Generator().manual_seed(7 + C)
+    src = torch.randn(4, C, 400, generator=g)
+    mix = torch.randn(4, C, C, generator=g) * 0.3 + torch.eye(C)[torch.randperm(C, generator=g)]      # estimates = permuted, leaky sources
+    est0 = torch.einsum("bij,bjl->bil", mix, src) + 0.1 * torch.randn(4, C, 400, generator=g)
+    lengths = torch.tensor([400, 399, 123, 57])
+    a, b = est0.clone().requires_grad_(True), est0.clone().requires_grad_(True)
+    mine = si_snr_with_pit(a, src.clone(), lengths)
+    ref = gu.SiSNR_With_Pit()(b * 1.0, src.clone(), lengths)          # the reference masks its argument in place (:435): hand it a non-leaf
+    assert torch.allclose(mine, ref, atol=1e-5), (float(mine), float(ref))
+    mine.backward(); ref.backward()
+    assert torch.allclose(a.grad, b.grad, atol=1e-6 + 1e-4 * float(b.grad.abs().max()))
