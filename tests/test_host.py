@@ -78,6 +78,9 @@ def test_reference_config_json_builds_module():
     from models.voicesplit.model import VoiceSplit
     m = VoiceSplit(c)
     assert m.dims == synth.make_dims(601, 256, 400, 600, 601)
+    # the restated loader reads the reference's own config.json to the same dict as the reference's load_config
+    _, _, gu = ref_import.load()
+    assert dict(gu.load_config(os.path.join(ref_import.REF_ROOT, "config.json"))) == dict(c)
 
 
 def test_cabi_exports_every_declared_symbol():
