@@ -230,3 +230,24 @@ def test_every_entry_point_rejects_a_null_engine_without_crashing():
                  lib.vs_loss_workspace_bytes(N, 1, 2), lib.vs_encoder_workspace_bytes(N, 1, 1, 1)):
         assert size == 0
     assert lib.vs_engine_destroy(N) == 0 and lib.vs_last_launch_count(N) == 0 and lib.vs_profile_read(N, 0, None, None) == 0
+
+
+def test_bench_algorithmic_flops_are_the_survey_figures():
+    """roofline.achieved is algorithmic FLOPs / time: the per-utterance figures bench.py uses are SURVEY.md 8(d)'s (2 x MAC, forward),
+    with the d-vector folded into a per-utterance gate bias (the smaller of the survey's two input-projection figures)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    want = {(301, 601): dict(conv=195.96, conv5x5_layer=37.049, lstm_input_proj=9.26, lstm_recurrence=0.771, fc=0.506, total=(206.4, 207.0)),
+            (601, 257): dict(conv=167.32, conv5x5_layer=31.63, lstm_input_proj=7.91, lstm_recurrence=1.54, fc=0.762, total=(177.5, 178.51))}
+    for (T, F), w in want.items():
+        f = b.flops_per_utt(T, F)
+        for k, v in w.items():
+            if k == "total":
+                assert v[0] <= f[k] / 1e9 <= v[1], (T, F, k, f[k])
+            else:
+                assert abs(f[k] / 1e9 - v) <= 0.006 * v, (T, F, k, f[k])
+        assert f["total"] == f["conv"] + f["lstm"] + f["fc"] and f["lstm"] == f["lstm_input_proj"] + f["lstm_recurrence"]
+    assert b.padded_f(257) == 264 and b.padded_f(601) == 608
