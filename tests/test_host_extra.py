@@ -299,3 +299,20 @@ def test_product_code_never_touches_the_oracle():
 def _includes_oracle(text):
     import re
     return re.search(r'#include\s+["<][^">]*oracle', text) is not None
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """Launched the way the driver launches N > 1 (torch.distributed.run, one process per GPU slot): rank 0 alone measures and prints,
+    the other ranks exit 0 without work."""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29500 + os.getpid() % 400
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--frames", "41", "--freq", "33"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
